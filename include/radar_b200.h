@@ -1,0 +1,214 @@
+/*
+ * radar_b200.h -- C ABI of libradar_b200.so: the B200-native (sm_100a) per-frame detection chain
+ *
+ *     int16 DDC unpack -> pulse compression -> MTD (Kaiser, slow-time FFT, fftshift, |.|)
+ *                      -> zero-velocity suppression -> 2-D CA-CFAR -> detection list
+ *
+ * Drop-in boundary for the MATLAB functions of XuZerui2023/Radar-Signal-Process.  Each entry point
+ * names the reference interface it replaces (file:line, relative to the reference root;
+ * MP = MatlabProcess_xuzerui, CW = MatlabProcess_xuzerui/CFAR_WangCai).  The MEX gateways in mex/
+ * bind exactly these symbols; INTEGRATION.md shows the reference-side stubs.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no exceptions cross the boundary.
+ *   - every call returns an rb200_status (0 = OK); rb200_last_error() gives the text.
+ *   - "_z" entry points take MATLAB split-complex double, column-major (row index fastest);
+ *     "_d" entry points take real double column-major.  Host pointers only.  Conversion to the
+ *     device's float32 layout happens on the device, not on the host.
+ *   - a context is bound to one CUDA device and one stream; it is not thread-safe; distinct
+ *     contexts are independent (one per rank / per MATLAB session).
+ *   - the caller owns every buffer it passes; the library owns only context-internal scratch.
+ *   - there is no CPU fallback: without a CUDA device rb200_create() fails with RB200_ERR_CUDA.
+ */
+#ifndef RADAR_B200_H
+#define RADAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB200_VERSION_MAJOR 0
+#define RB200_VERSION_MINOR 1
+
+typedef struct rb200_ctx rb200_ctx;
+
+typedef enum {
+    RB200_OK = 0,
+    RB200_ERR_ARG = 1,          /* bad argument (null pointer, negative size, unknown enum)           */
+    RB200_ERR_CUDA = 2,         /* CUDA runtime error (sticky; text in rb200_last_error)              */
+    RB200_ERR_INDEX = 3,        /* the M-code would raise "Index exceeds array bounds"                */
+    RB200_ERR_DIM_MISMATCH = 4, /* the M-code would raise a dimension-mismatch error                  */
+    RB200_ERR_NO_WAVEFORM = 5,  /* rb200_set_waveform() has not been called                           */
+    RB200_ERR_UNSUPPORTED = 6,  /* outside the implemented envelope (documented per call)             */
+    RB200_ERR_OVERFLOW = 7      /* detection list truncated: *n_det holds the true count              */
+} rb200_status;
+
+/* ---- chain geometry and detector parameters --------------------------------------------------
+ * Mirrors the literals the reference scatters through its scripts: geometry
+ * (MP/fun_MTD_produce.m:8,41-44), Kaiser beta (MP/fun_Process_MTD.m:13), zero-velocity divisor
+ * (MP/fun_0v_pressing.m:4-6 -> 150, CW/fun_0v_pressing.m:5 -> 20), MTI lag (MP/fun_Process_MTI.m:20-21),
+ * CFAR parameters (CW/main_cfar.m:40-58; argument order of CW/executeCFAR.m:1-2).                 */
+typedef struct {
+    int32_t struct_size;     /* = sizeof(rb200_config), for ABI evolution                            */
+    int32_t n_prt;           /* P: PRTs per CPI (slow time)                                          */
+    int32_t n_range;         /* R: range cells per PRT (fast time)                                   */
+    int32_t n_lanes;         /* C: channels/beams interleaved in the wire format                     */
+    int32_t max_cpi;         /* largest n_cpi a single rb200_chain_i16 call will pass                */
+    int32_t max_det;         /* capacity of the device detection list per call                       */
+    int32_t zero_v_div;      /* 150 (MP/, MTD/), 20 (CW/), 0 = no zero-velocity suppression          */
+    int32_t mti_lag;         /* 0 = off; 30 = fun_Process_MTI, applied after PC, before the window   */
+    double  kaiser_beta;     /* 8                                                                    */
+    int32_t cfar_ref_r, cfar_guard_r, cfar_method_r;   /* range axis: ref cells, guard cells, 0=GO 1=SO */
+    int32_t cfar_ref_v, cfar_guard_v, cfar_method_v;   /* velocity axis                              */
+    double  cfar_t_r, cfar_t_v;                        /* threshold factors                          */
+    int32_t cfar_n0;         /* MTD_0_num: rows 1..n0+1 and the last n0 are not tested               */
+    int32_t cfar_range_stage;/* rCFARDetect_Flag                                                     */
+    int32_t chunk_cpi;       /* CPIs per PC->MTD->CFAR pass (L2 residency); 0 = library default      */
+    int32_t reserved;
+} rb200_config;
+
+/* ---- waveform plan ----------------------------------------------------------------------------
+ * One entry per waveform segment of a PRT (MP/fun_lss_pulse_compression.m:6-8,14-16,31,36-37;
+ * MTD/fun_lss_pulse_compression.m:23-25,47-51,58-65).                                            */
+typedef enum {
+    RB200_SEG_MF = 0,   /* fun_pulse_compression(taps, x) then (L : L+out_len-1)                     */
+    RB200_SEG_FIR = 1   /* filter(taps,1,x) * scale                                                  */
+} rb200_seg_kind;
+
+typedef enum {
+    RB200_ALIGN_LEADING_EDGE = 0, /* MF: output n <-> lag n (peak at the echo's first sample)        */
+    RB200_ALIGN_DELAYED = 1,      /* FIR, MP/ 5-arg rule: causal output left delayed (:31)           */
+    RB200_ALIGN_GRPDELAY = 2      /* FIR, MTD/ 9-arg rule: circshift(y,-round(mean(grpdelay))) (:47-51) */
+} rb200_seg_align;
+
+typedef struct {
+    int32_t in_start, in_len;    /* 0-based first column and length of the input slice               */
+    int32_t out_start, out_len;  /* where the result lands in the output PRT (out_len <= in_len)     */
+    int32_t kind;                /* rb200_seg_kind                                                   */
+    int32_t align;               /* rb200_seg_align                                                  */
+    int32_t n_taps;
+    int32_t reserved;
+    const double* taps_re;       /* MF: reference pulse s0 (un-flipped, un-conjugated); FIR: b       */
+    const double* taps_im;       /* may be NULL (real taps)                                          */
+    double scale;                /* multiplies the segment output (FIR: 1/1.2; MF: 1)                */
+} rb200_segment;
+
+/* One detection.  kind bit0 = velocity-stage hit (cfarResultFlag_MatrixV), bit1 = final 2-D flag
+ * (cfarResultFlag_Matrix).  v and r are 0-based; the gateways add 1 for MATLAB.                   */
+typedef struct {
+    uint32_t cpi;
+    uint32_t r;
+    uint16_t v;
+    uint8_t  lane;
+    uint8_t  kind;
+    float    amp;
+} rb200_det;
+
+#define RB200_DET_V    1u
+#define RB200_DET_2D   2u
+
+/* ---- lifetime ---------------------------------------------------------------------------------*/
+int rb200_version(void);                                      /* major*100 + minor                  */
+int rb200_create(rb200_ctx** out, int device, const rb200_config* cfg);
+int rb200_destroy(rb200_ctx* ctx);
+const char* rb200_last_error(const rb200_ctx* ctx);           /* NULL ctx -> last create() error    */
+int rb200_get_config(const rb200_ctx* ctx, rb200_config* out);
+int rb200_set_cfar(rb200_ctx* ctx, const rb200_config* cfg);  /* update only the cfar_* fields      */
+
+/* Precompute and keep resident the reference spectra of every segment.  Replaces the per-PRT
+ * fft(h,n) of MP/fun_pulse_compression.m:20.                                                      */
+int rb200_set_waveform(rb200_ctx* ctx, const rb200_segment* segs, int nseg);
+
+/* iSTC gain curve in dB, zero-extended to n_range; n = 0 disables.  MP/fun_iSTC.m:6-9,14.         */
+int rb200_set_stc(rb200_ctx* ctx, const double* stc_db, int n);
+
+/* ---- MATLAB-layout entry points (one per reference function) -----------------------------------*/
+
+/* signal_PC = fun_pulse_compression(s0, s_echo)        MP/fun_pulse_compression.m:1
+ * out_* hold L+M-1 samples.                                                                       */
+int rb200_pulse_compression_z(rb200_ctx* ctx, const double* s0_re, const double* s0_im, int L,
+                              const double* echo_re, const double* echo_im, int M,
+                              double* out_re, double* out_im);
+
+/* s_PC_0 = fun_lss_pulse_compression(echo, ...)        MP/fun_lss_pulse_compression.m:3,
+ *                                                      MTD/fun_lss_pulse_compression.m:17
+ * Uses the plan given to rb200_set_waveform.  echo and out are P x R column-major.                */
+int rb200_lss_pulse_compression_z(rb200_ctx* ctx, const double* echo_re, const double* echo_im,
+                                  int P, int R, double* out_re, double* out_im);
+
+/* MTD_Signal = fun_Process_MTD(ProSignal, Len_PRT, Num_PRTperFrame)   MP/fun_Process_MTD.m:3
+ * ProSignal is rows x cols; out is Num_PRTperFrame x Len_PRT real.                                */
+int rb200_process_mtd_z(rb200_ctx* ctx, const double* re, const double* im, int rows, int cols,
+                        int len_prt, int num_prt, double beta, double* out);
+
+/* MTD = fun_0v_pressing(MTD)                           MP/fun_0v_pressing.m:2 (div 150),
+ *                                                      CW/fun_0v_pressing.m:2 (div 20)            */
+int rb200_zero_v_pressing_d(rb200_ctx* ctx, const double* mtd, int P, int R, int div, double* out);
+
+/* MTD_Signal = fun_MTD_produce(echo[,params])          MP/fun_MTD_produce.m:3, MTD/fun_MTD_produce.m:12
+ * PC (current plan) -> [MTI] -> MTD -> 0-v on a P x R column-major frame; out is P x R real.      */
+int rb200_mtd_produce_z(rb200_ctx* ctx, const double* echo_re, const double* echo_im, int P, int R,
+                        double beta, int zero_v_div, double* out);
+
+/* F = Function_CFAR1D_sub(data, ref, save, T, method)  CW/Function_CFAR1D_sub.m:1
+ * data/out are rows x cols column-major; detection runs along columns index (second dim).         */
+int rb200_cfar1d_sub_d(rb200_ctx* ctx, const double* data, int rows, int cols, int ref, int guard,
+                       double T, int method, double* out);
+
+/* F = Function_CFAR1D_sub_fixCells(data, ref, save, T, method, rowCellsFix, colCellsFix)
+ *                                                      CW/Function_CFAR1D_sub_fixCells.m:1
+ * rows_fix / cols_fix are 1-based like the M arguments.                                           */
+int rb200_cfar1d_fix_d(rb200_ctx* ctx, const double* data, int rows, int cols, int ref, int guard,
+                       double T, int method, const int32_t* rows_fix, int n_rows_fix,
+                       const int32_t* cols_fix, int n_cols_fix, double* out);
+
+/* [F, FV] = executeCFAR(mtd, refR, saveR, T_R, methR, refV, saveV, T_V, methV, n0, rFlag)
+ *                                                      CW/executeCFAR.m:1
+ * mtd, out_flag, out_flag_v are V x R column-major; out_flag_v may be NULL.                       */
+int rb200_execute_cfar_d(rb200_ctx* ctx, const double* mtd, int V, int R,
+                         int ref_r, int guard_r, double t_r, int method_r,
+                         int ref_v, int guard_v, double t_v, int method_v,
+                         int n0, int range_stage, double* out_flag, double* out_flag_v);
+
+/* ---- batched wire-format entry points (benchmark / multi-GPU path) ------------------------------
+ * raw: int16 [cpi][prt][range][lane][I,Q]  (FrameDataRead_xzr.m:150-156 per PRT, payload only).   */
+
+/* Parity/debug: unpacked samples as float2 [cpi][lane][prt][range] (re,im interleaved). Host ptrs. */
+int rb200_unpack_ddc_i16(rb200_ctx* ctx, const int16_t* raw, int n_cpi, float* out_ri);
+
+/* The whole chain for n_cpi CPIs.  raw / rdm_out / dets may each be host or device pointers
+ * (detected with cudaPointerGetAttributes); rdm_out ([cpi][lane][v][range] float) and dets may be
+ * NULL.  *n_det (host int) receives the number of detections found; at most max_det are stored
+ * (RB200_ERR_OVERFLOW if more).  stream: a cudaStream_t cast to void*, NULL = the context stream.
+ * The call returns after the work has completed on the stream.                                    */
+int rb200_chain_i16(rb200_ctx* ctx, const int16_t* raw, int n_cpi, float* rdm_out,
+                    rb200_det* dets, int* n_det, void* stream);
+
+/* Same as rb200_chain_i16 with device-resident raw/rdm_out, but only enqueues the kernels (no
+ * synchronisation, no D2H): used to time the device chain with caller-owned events.  The
+ * detection count/list stay in context memory until rb200_chain_fetch.                            */
+int rb200_chain_enqueue(rb200_ctx* ctx, const int16_t* raw_dev, int n_cpi, float* rdm_dev, void* stream);
+int rb200_chain_fetch(rb200_ctx* ctx, rb200_det* dets_host, int* n_det);
+
+/* Device-side intermediates of the last chain call (parity tests): pulse-compressed samples as
+ * float2 [cpi][lane][prt][range] for the last processed chunk.                                    */
+int rb200_debug_fetch_pc(rb200_ctx* ctx, int cpi_in_chunk, float* out_ri);
+
+/* Milliseconds between the first and last kernel of the last chain call (CUDA events).            */
+int rb200_last_device_ms(const rb200_ctx* ctx, float* ms);
+/* Number of kernels the last call launched (bench.py's gpu_launches).                             */
+int rb200_last_launch_count(const rb200_ctx* ctx, int* n);
+
+/* ---- "next" rows ---------------------------------------------------------*/
+
+/* f1: DBF weighting fused into the unpack: beams = sig_C * W.' (FrameDataRead_xzr.m:158).
+ * w_re/w_im: n_beams x n_lanes column-major (DBF_coeffs_data_C); n_beams = 0 disables.  When
+ * enabled the chain's lane count downstream of the unpack is n_beams.                             */
+int rb200_set_dbf(rb200_ctx* ctx, const double* w_re, const double* w_im, int n_beams);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADAR_B200_H */

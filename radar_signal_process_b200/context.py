@@ -1,0 +1,216 @@
+"""Context: one rb200_ctx (one CUDA device, one stream) behind a Python object."""
+import ctypes as C
+
+import numpy as np
+
+from . import _binding as B
+
+
+def _split(z):
+    """complex/real ndarray -> (re, im|None) contiguous float64 in MATLAB (column-major) element order."""
+    z = np.asarray(z)
+    if np.iscomplexobj(z):
+        return np.asfortranarray(z.real, dtype=np.float64), np.asfortranarray(z.imag, dtype=np.float64)
+    return np.asfortranarray(z, dtype=np.float64), None
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+class Context:
+    def __init__(self, device=0, **cfg):
+        self._lib = B.load()
+        self._h = C.c_void_p()
+        self.cfg = B.default_config(**cfg)
+        st = self._lib.rb200_create(C.byref(self._h), int(device), C.byref(self.cfg))
+        if st != B.OK:
+            text = self._lib.rb200_last_error(None)
+            self._h = C.c_void_p()
+            raise B.RadarB200Error(st, text.decode() if text else "")
+        self._keep = None
+        self.device = int(device)
+
+    # ---- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.rb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, st):
+        B.raise_for(st, self._h)
+
+    # ---- configuration ----------------------------------------------------------------------------
+    def set_waveform(self, segments):
+        arr = (B.Segment * len(segments))()
+        keep = []
+        for i, s in enumerate(segments):
+            taps = np.asarray(s["taps"], dtype=np.complex128).ravel()
+            re = np.ascontiguousarray(taps.real)
+            im = np.ascontiguousarray(taps.imag)
+            keep += [re, im]
+            a = arr[i]
+            a.in_start, a.in_len, a.out_start, a.out_len = s["in_start"], s["in_len"], s["out_start"], s["out_len"]
+            a.kind, a.align, a.n_taps = s["kind"], s["align"], taps.size
+            a.taps_re, a.taps_im, a.scale = _fptr(re), _fptr(im), s.get("scale", 1.0)
+        self._ck(self._lib.rb200_set_waveform(self._h, arr, len(segments)))
+
+    def set_stc(self, stc_db):
+        if stc_db is None or len(stc_db) == 0:
+            self._ck(self._lib.rb200_set_stc(self._h, None, 0))
+            return
+        a = np.ascontiguousarray(stc_db, dtype=np.float64)
+        self._ck(self._lib.rb200_set_stc(self._h, _fptr(a), a.size))
+
+    def set_cfar(self, refR, saveR, T_R, methR, refV, saveV, T_V, methV, n0, rflag):
+        c = self.cfg
+        c.cfar_ref_r, c.cfar_guard_r, c.cfar_t_r, c.cfar_method_r = int(refR), int(saveR), float(T_R), int(methR)
+        c.cfar_ref_v, c.cfar_guard_v, c.cfar_t_v, c.cfar_method_v = int(refV), int(saveV), float(T_V), int(methV)
+        c.cfar_n0, c.cfar_range_stage = int(n0), int(bool(rflag))
+        self._ck(self._lib.rb200_set_cfar(self._h, C.byref(c)))
+
+    # ---- MATLAB-layout entry points ------------------------------------------------------------------
+    def pulse_compression(self, s0, s_echo):
+        s0 = np.asarray(s0).ravel()
+        x = np.asarray(s_echo).ravel()
+        sre, sim = _split(s0)
+        xre, xim = _split(x)
+        n = s0.size + x.size - 1
+        ore, oim = np.zeros(max(n, 0)), np.zeros(max(n, 0))
+        self._ck(self._lib.rb200_pulse_compression_z(self._h, _fptr(sre), _fptr(sim), s0.size, _fptr(xre), _fptr(xim), x.size,
+                                                     _fptr(ore), _fptr(oim)))
+        return ore + 1j * oim
+
+    def lss_pulse_compression(self, echo):
+        echo = np.atleast_2d(echo)
+        P, R = echo.shape
+        re, im = _split(echo)
+        ore = np.zeros((P, R), order="F")
+        oim = np.zeros((P, R), order="F")
+        self._ck(self._lib.rb200_lss_pulse_compression_z(self._h, _fptr(re), _fptr(im), P, R, _fptr(ore), _fptr(oim)))
+        return ore + 1j * oim
+
+    def process_mtd(self, x, len_prt, num_prt, beta=8.0):
+        x = np.atleast_2d(x)
+        rows, cols = x.shape
+        re, im = _split(x)
+        out = np.zeros((int(num_prt), int(len_prt)), order="F")
+        self._ck(self._lib.rb200_process_mtd_z(self._h, _fptr(re), _fptr(im), rows, cols, int(len_prt), int(num_prt), float(beta), _fptr(out)))
+        return out
+
+    def zero_v_pressing(self, mtd, div=150):
+        mtd = np.asfortranarray(np.atleast_2d(mtd), dtype=np.float64)
+        out = np.zeros(mtd.shape, order="F")
+        self._ck(self._lib.rb200_zero_v_pressing_d(self._h, _fptr(mtd), mtd.shape[0], mtd.shape[1], int(div), _fptr(out)))
+        return out
+
+    def mtd_produce(self, echo, beta=8.0, zero_v_div=150):
+        echo = np.atleast_2d(echo)
+        P, R = echo.shape
+        re, im = _split(echo)
+        out = np.zeros((P, R), order="F")
+        self._ck(self._lib.rb200_mtd_produce_z(self._h, _fptr(re), _fptr(im), P, R, float(beta), int(zero_v_div), _fptr(out)))
+        return out
+
+    def cfar1d_sub(self, data, ref, guard, T, method):
+        d = np.asfortranarray(np.atleast_2d(data), dtype=np.float64)
+        out = np.zeros(d.shape, order="F")
+        self._ck(self._lib.rb200_cfar1d_sub_d(self._h, _fptr(d), d.shape[0], d.shape[1], int(ref), int(guard), float(T), int(method), _fptr(out)))
+        return out
+
+    def cfar1d_fix(self, data, ref, guard, T, method, rows_fix, cols_fix):
+        d = np.asfortranarray(np.atleast_2d(data), dtype=np.float64)
+        out = np.zeros(d.shape, order="F")
+        rf = np.ascontiguousarray(np.atleast_1d(rows_fix), dtype=np.int32)
+        cf = np.ascontiguousarray(np.atleast_1d(cols_fix), dtype=np.int32)
+        ip = C.POINTER(C.c_int32)
+        self._ck(self._lib.rb200_cfar1d_fix_d(self._h, _fptr(d), d.shape[0], d.shape[1], int(ref), int(guard), float(T), int(method),
+                                              rf.ctypes.data_as(ip), rf.size, cf.ctypes.data_as(ip), cf.size, _fptr(out)))
+        return out
+
+    def execute_cfar(self, mtd, refR, saveR, T_R, methR, refV, saveV, T_V, methV, n0, rflag):
+        d = np.asfortranarray(np.atleast_2d(mtd), dtype=np.float64)
+        f = np.zeros(d.shape, order="F")
+        fv = np.zeros(d.shape, order="F")
+        self._ck(self._lib.rb200_execute_cfar_d(self._h, _fptr(d), d.shape[0], d.shape[1], int(refR), int(saveR), float(T_R), int(methR),
+                                                int(refV), int(saveV), float(T_V), int(methV), int(n0), int(bool(rflag)), _fptr(f), _fptr(fv)))
+        return f, fv
+
+    # ---- batched wire-format entry points ---------------------------------------------------------------
+    def _cells(self, n_cpi):
+        c = self.cfg
+        return n_cpi * c.n_prt * c.n_range * c.n_lanes
+
+    def unpack(self, raw, n_cpi):
+        c = self.cfg
+        raw = np.ascontiguousarray(raw, dtype=np.int16)
+        assert raw.size == self._cells(n_cpi) * 2
+        out = np.zeros((n_cpi, c.n_lanes, c.n_prt, c.n_range), dtype=np.complex64)
+        self._ck(self._lib.rb200_unpack_ddc_i16(self._h, raw.ctypes.data, n_cpi, out.ctypes.data))
+        return out
+
+    def chain(self, raw, n_cpi, want_rdm=True, allow_overflow=False):
+        """Host-buffer chain call: numpy int16 wire array in, (rdm float32 [cpi][lane][v][r] | None, dets) out."""
+        c = self.cfg
+        raw = np.ascontiguousarray(raw, dtype=np.int16)
+        assert raw.size == self._cells(n_cpi) * 2, "raw has the wrong number of samples for the configured geometry"
+        rdm = np.zeros((n_cpi, c.n_lanes, c.n_prt, c.n_range), dtype=np.float32) if want_rdm else None
+        dets = np.zeros(c.max_det, dtype=B.DET_DTYPE)
+        n = C.c_int(0)
+        st = self._lib.rb200_chain_i16(self._h, raw.ctypes.data, n_cpi, rdm.ctypes.data if want_rdm else None,
+                                       dets.ctypes.data, C.byref(n), None)
+        if not (st == B.ERR_OVERFLOW and allow_overflow):
+            self._ck(st)
+        return rdm, dets[: min(n.value, c.max_det)].copy(), n.value
+
+    def chain_ptr(self, raw_ptr, n_cpi, rdm_ptr, dets_ptr, stream=None):
+        """Raw-pointer chain call (host or device addresses as ints); returns (status, n_det)."""
+        n = C.c_int(0)
+        st = self._lib.rb200_chain_i16(self._h, raw_ptr, n_cpi, rdm_ptr, dets_ptr, C.byref(n), stream)
+        return st, n.value
+
+    def chain_enqueue(self, raw_dev_ptr, n_cpi, rdm_dev_ptr, stream=None):
+        self._ck(self._lib.rb200_chain_enqueue(self._h, raw_dev_ptr, n_cpi, rdm_dev_ptr, stream))
+
+    def chain_fetch(self, allow_overflow=False):
+        dets = np.zeros(self.cfg.max_det, dtype=B.DET_DTYPE)
+        n = C.c_int(0)
+        st = self._lib.rb200_chain_fetch(self._h, dets.ctypes.data, C.byref(n))
+        if not (st == B.ERR_OVERFLOW and allow_overflow):
+            self._ck(st)
+        return dets[: min(n.value, self.cfg.max_det)].copy(), n.value
+
+    def debug_fetch_pc(self, cpi_in_chunk=0):
+        c = self.cfg
+        out = np.zeros((c.n_lanes, c.n_prt, c.n_range), dtype=np.complex64)
+        self._ck(self._lib.rb200_debug_fetch_pc(self._h, int(cpi_in_chunk), out.ctypes.data))
+        return out
+
+    def last_device_ms(self):
+        ms = C.c_float(0)
+        self._ck(self._lib.rb200_last_device_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def last_launch_count(self):
+        n = C.c_int(0)
+        self._ck(self._lib.rb200_last_launch_count(self._h, C.byref(n)))
+        return n.value
+
+
+def dets_to_flags(dets, n_cpi, n_lanes, V, R):
+    """Rebuild executeCFAR's two dense 0/1 matrices per (cpi, lane) from a detection list."""
+    flag = np.zeros((n_cpi, n_lanes, V, R), dtype=np.float64)
+    flagv = np.zeros((n_cpi, n_lanes, V, R), dtype=np.float64)
+    d2 = dets[(dets["kind"] & B.DET_2D) != 0]
+    dv = dets[(dets["kind"] & B.DET_V) != 0]
+    flag[d2["cpi"], d2["lane"], d2["v"], d2["r"]] = 1.0
+    flagv[dv["cpi"], dv["lane"], dv["v"], dv["r"]] = 1.0
+    return flag, flagv

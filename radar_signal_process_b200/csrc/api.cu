@@ -1,0 +1,1028 @@
+// api.cu -- context, plans and the extern "C" entry points of libradar_b200.so (include/radar_b200.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/radar_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace rb;
+typedef std::complex<double> cd;
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// iterative radix-2 FFT in double (host, plan-time only; n is a power of two)
+void host_fft_pow2(std::vector<cd>& a) {
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const double ang = -2.0 * M_PI / (double)len;
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const cd w = std::polar(1.0, ang * (double)k);
+                const cd u = a[i + k], v = a[i + k + len / 2] * w;
+                a[i + k] = u + v;
+                a[i + k + len / 2] = u - v;
+            }
+    }
+}
+
+long mround(double x) { return (long)(x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5)); }
+
+// kaiser(n, beta) of the Signal Processing Toolbox (MP/fun_Process_MTD.m:13-14)
+std::vector<double> kaiser_window(int n, double beta) {
+    std::vector<double> w(n, 1.0);
+    if (n <= 1) return w;
+    const double denom = std::cyl_bessel_i(0.0, std::fabs(beta));
+    const double alpha = (n - 1) / 2.0;
+    for (int k = 0; k < n; ++k) {
+        const double r = (k - alpha) / alpha;
+        w[k] = std::cyl_bessel_i(0.0, std::fabs(beta) * std::sqrt(std::max(0.0, 1.0 - r * r))) / denom;
+    }
+    return w;
+}
+
+// round(mean(grpdelay(b))) for a real FIR (MTD/fun_lss_pulse_compression.m:47), 512 points on [0,pi)
+int grpdelay_mean_round(const std::vector<double>& b) {
+    double acc = 0, babs = 0;
+    for (double x : b) babs += std::fabs(x);
+    for (int i = 0; i < 512; ++i) {
+        const double w = M_PI * i / 512.0;
+        cd num = 0, den = 0;
+        for (size_t k = 0; k < b.size(); ++k) {
+            const cd e = std::polar(1.0, -w * (double)k);
+            num += (double)k * b[k] * e;
+            den += b[k] * e;
+        }
+        if (std::abs(den) < 10 * 2.220446049250313e-16 * std::max(1.0, babs)) continue;   // singular -> 0
+        acc += (num / den).real();
+    }
+    return (int)mround(acc / 512.0);
+}
+
+struct SegPlan {
+    PcSegDev d;
+    int nt;     // FFT tile (0 = time-domain fallback)
+};
+
+struct ClassPlan {   // all segments sharing one FFT tile size
+    int nt = 0;
+    int n_tiles = 0;
+    DevBuf tiles, tw;
+};
+
+struct Plan {
+    std::vector<SegPlan> segs;
+    std::vector<ClassPlan> classes;
+    DevBuf hperm, taps;
+    std::vector<std::pair<int, int>> out_ranges;   // sorted [start, end) written by segments
+    int max_in_end = 0, max_out_end = 0;
+    bool valid = false;
+    void release() {
+        for (auto& c : classes) { c.tiles.release(); c.tw.release(); }
+        classes.clear();
+        hperm.release();
+        taps.release();
+        segs.clear();
+        out_ranges.clear();
+        valid = false;
+    }
+};
+
+struct MtdPlan {
+    int P = 0;
+    double beta = 0;
+    DevBuf window, tw;
+    int n_stages = 0;
+    int radix[16];
+};
+
+}  // namespace
+
+struct rb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    rb200_config cfg;
+    std::string err;
+    Plan plan;
+    std::map<std::pair<int, long long>, MtdPlan*> mtd_plans;
+    DevBuf gain;
+    int gain_n = 0;
+    // chain buffers
+    DevBuf raw, pc, rdm, dets_v, dets_2d, counters, vmask, errflag;
+    // MATLAB-layout scratch
+    DevBuf s_in_re, s_in_im, s_a, s_b, s_c, s_out_re, s_out_im, s_u8a, s_u8b, s_idx;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool have_timing = false;
+    int launches = 0;
+    int last_chunk_cpis = 0;
+    // pinned staging for host detections
+    rb200_det* h_dets = nullptr;
+    int* h_counts = nullptr;
+};
+
+static std::string g_create_error;
+
+#define CK(ctx, call)                                                                                 \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            char buf__[512];                                                                          \
+            snprintf(buf__, sizeof buf__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            (ctx)->err = buf__;                                                                       \
+            return RB200_ERR_CUDA;                                                                    \
+        }                                                                                             \
+    } while (0)
+
+static int fail(rb200_ctx* c, int code, const char* msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plans
+// ---------------------------------------------------------------------------------------------
+static int choose_nt(int L) {
+    const char* env = getenv("RB200_PC_NT");
+    if (env) {
+        const int nt = atoi(env);
+        if ((nt == 256 || nt == 512 || nt == 4096) && nt - L + 1 >= nt / 8) return nt;
+    }
+    // estimated butterfly flops per transformed point (forward + inverse + spectrum multiply)
+    const int cand[3] = {256, 512, 4096};
+    const double cost[3] = {59.0, 75.0, 92.0};
+    int best = 0;
+    double bestc = 1e300;
+    for (int i = 0; i < 3; ++i) {
+        const int V = cand[i] - L + 1;
+        if (V < cand[i] / 8) continue;
+        const double c = cost[i] * cand[i] / V;
+        if (c < bestc) { bestc = c; best = cand[i]; }
+    }
+    return best;
+}
+
+static int build_plan(rb200_ctx* ctx, Plan& plan, const rb200_segment* segs, int nseg) {
+    plan.release();
+    if (nseg < 1 || nseg > kMaxSegs || !segs) return fail(ctx, RB200_ERR_ARG, "set_waveform: need 1..8 segments");
+    std::vector<std::vector<cd>> corr_taps(nseg);   // t[k] of the correlation form
+    std::vector<float2> taps_all;
+    size_t h_total = 0;
+    for (int i = 0; i < nseg; ++i) {
+        const rb200_segment& s = segs[i];
+        if (s.n_taps < 1 || !s.taps_re || s.in_len < 0 || s.out_len < 0 || s.in_start < 0 || s.out_start < 0)
+            return fail(ctx, RB200_ERR_ARG, "set_waveform: bad segment");
+        const int L = s.n_taps;
+        std::vector<cd> raw(L);
+        for (int k = 0; k < L; ++k) raw[k] = cd(s.taps_re[k], s.taps_im ? s.taps_im[k] : 0.0);
+        SegPlan sp;
+        memset(&sp, 0, sizeof sp);
+        sp.d.in_start = s.in_start;
+        sp.d.in_len = s.in_len;
+        sp.d.out_start = s.out_start;
+        sp.d.out_len = s.out_len;
+        sp.d.n_taps = L;
+        if (s.kind == RB200_SEG_MF) {
+            if (s.align != RB200_ALIGN_LEADING_EDGE) return fail(ctx, RB200_ERR_ARG, "set_waveform: MF segments use LEADING_EDGE");
+            corr_taps[i] = raw;                       // y[n] = sum x[n+k] conj(s0[k])
+            sp.d.pre = 0;
+            sp.d.rot = 0;
+        } else if (s.kind == RB200_SEG_FIR) {
+            corr_taps[i].resize(L);                   // y[n] = sum_j x[n-(L-1)+j] b[L-1-j]
+            for (int j = 0; j < L; ++j) corr_taps[i][j] = std::conj(raw[L - 1 - j]);
+            sp.d.pre = L - 1;
+            sp.d.rot = 0;
+            if (s.align == RB200_ALIGN_GRPDELAY) {
+                std::vector<double> b(L);
+                for (int k = 0; k < L; ++k) b[k] = s.taps_re[k];
+                int d = grpdelay_mean_round(b);
+                if (s.out_len > 0) {
+                    d %= s.out_len;
+                    if (d < 0) d += s.out_len;
+                }
+                sp.d.rot = d;
+            } else if (s.align != RB200_ALIGN_DELAYED) {
+                return fail(ctx, RB200_ERR_ARG, "set_waveform: FIR segments use DELAYED or GRPDELAY");
+            }
+        } else {
+            return fail(ctx, RB200_ERR_ARG, "set_waveform: unknown segment kind");
+        }
+        sp.nt = choose_nt(L);
+        sp.d.t_off = (int)taps_all.size();
+        for (int k = 0; k < L; ++k) {
+            const cd t = corr_taps[i][k] * s.scale;    // direct kernel multiplies by conj(t) -> fold real scale
+            taps_all.push_back(make_float2((float)t.real(), (float)t.imag()));
+        }
+        if (sp.nt) {
+            sp.d.V = sp.nt - L + 1;
+            sp.d.h_off = (int)h_total;
+            h_total += sp.nt;
+        }
+        plan.segs.push_back(sp);
+        plan.max_in_end = std::max(plan.max_in_end, s.in_start + s.in_len);
+        plan.max_out_end = std::max(plan.max_out_end, s.out_start + s.out_len);
+        plan.out_ranges.push_back({s.out_start, s.out_start + s.out_len});
+    }
+    std::sort(plan.out_ranges.begin(), plan.out_ranges.end());
+    // spectra
+    std::vector<float2> hperm(std::max<size_t>(h_total, 1));
+    for (int i = 0; i < nseg; ++i) {
+        const SegPlan& sp = plan.segs[i];
+        if (!sp.nt) continue;
+        const int NT = sp.nt;
+        std::vector<cd> a(NT, cd(0, 0));
+        for (int k = 0; k < sp.d.n_taps; ++k) a[k] = corr_taps[i][k];
+        host_fft_pow2(a);
+        const int R = (NT == 512) ? 8 : 16;
+        int S = 0;
+        for (int n = NT; n > 1; n /= R) ++S;
+        for (int pos = 0; pos < NT; ++pos) {
+            int f = 0, mul = 1, div = NT / R;
+            for (int d = 0; d < S; ++d) {
+                f += ((pos / div) % R) * mul;
+                mul *= R;
+                div /= R;
+            }
+            const cd h = std::conj(a[f]) * (segs[i].scale / (double)NT);
+            hperm[sp.d.h_off + pos] = make_float2((float)h.real(), (float)h.imag());
+        }
+    }
+    CK(ctx, plan.hperm.ensure(hperm.size() * sizeof(float2)));
+    CK(ctx, cudaMemcpyAsync(plan.hperm.p, hperm.data(), hperm.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, plan.taps.ensure(std::max<size_t>(taps_all.size(), 1) * sizeof(float2)));
+    CK(ctx, cudaMemcpyAsync(plan.taps.p, taps_all.data(), taps_all.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    // tile lists and twiddles per class
+    const int nts[3] = {256, 512, 4096};
+    for (int ci = 0; ci < 3; ++ci) {
+        std::vector<int2> tiles;
+        for (int i = 0; i < nseg; ++i) {
+            const SegPlan& sp = plan.segs[i];
+            if (sp.nt != nts[ci] || sp.d.out_len == 0) continue;
+            const int nt_tiles = (sp.d.out_len + sp.d.V - 1) / sp.d.V;
+            for (int t = 0; t < nt_tiles; ++t) tiles.push_back(make_int2(i, t));
+        }
+        if (tiles.empty()) continue;
+        plan.classes.emplace_back();
+        ClassPlan& c = plan.classes.back();
+        c.nt = nts[ci];
+        c.n_tiles = (int)tiles.size();
+        CK(ctx, c.tiles.ensure(tiles.size() * sizeof(int2)));
+        CK(ctx, cudaMemcpyAsync(c.tiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<float2> tw(c.nt);
+        for (int m = 0; m < c.nt; ++m) {
+            const double a = -2.0 * M_PI * m / c.nt;
+            tw[m] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        CK(ctx, c.tw.ensure(tw.size() * sizeof(float2)));
+        CK(ctx, cudaMemcpyAsync(c.tw.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
+    plan.valid = true;
+    return RB200_OK;
+}
+
+// run pulse compression: `in` wire int16 (n_groups = cpi*P groups of C lanes) or planar float2 (n_lines lines)
+static int run_pc(rb200_ctx* ctx, const Plan& plan, bool wire, const void* in, float2* out, int R, int R_out,
+                  int C, int P, int n_groups_wire, int n_lines, const float* gain, cudaStream_t st) {
+    if (!plan.valid) return fail(ctx, RB200_ERR_NO_WAVEFORM, "no waveform plan: call rb200_set_waveform first");
+    if (plan.max_in_end > R) return fail(ctx, RB200_ERR_INDEX, "waveform segment exceeds the PRT length (Index exceeds array bounds)");
+    if (plan.max_out_end > R_out) return fail(ctx, RB200_ERR_INDEX, "waveform segment output exceeds the PRT length");
+    const size_t out_lines = wire ? (size_t)n_groups_wire * C : (size_t)n_lines;
+    // columns no segment writes stay zero (s_PC_0 = zeros(...))
+    int cur = 0;
+    for (auto& rg : plan.out_ranges) {
+        if (rg.first > cur) { CK(ctx, launch_pc_zero_cols(out, out_lines, R_out, cur, rg.first, st)); ctx->launches++; }
+        cur = std::max(cur, rg.second);
+    }
+    if (cur < R_out) { CK(ctx, launch_pc_zero_cols(out, out_lines, R_out, cur, R_out, st)); ctx->launches++; }
+    PcParams p;
+    memset(&p, 0, sizeof p);
+    p.in = in;
+    p.out = out;
+    p.hperm = plan.hperm.as<float2>();
+    p.gain = gain;
+    for (size_t i = 0; i < plan.segs.size(); ++i) p.segs[i] = plan.segs[i].d;
+    p.R = R;
+    p.R_out = R_out;
+    p.C = C;
+    p.P = P;
+    p.n_lines = n_lines;
+    for (auto& c : plan.classes) {
+        p.tw = c.tw.as<float2>();
+        p.tiles = c.tiles.as<int2>();
+        const int lt = pc_tile_lanes(c.nt, wire);
+        const int n_groups = wire ? n_groups_wire : (n_lines + lt - 1) / lt;
+        if (n_groups <= 0) continue;
+        CK(ctx, launch_pc_fft(c.nt, wire, p, c.n_tiles, n_groups, st));
+        ctx->launches++;
+    }
+    for (size_t i = 0; i < plan.segs.size(); ++i) {
+        if (plan.segs[i].nt || plan.segs[i].d.out_len == 0) continue;
+        const int lines = wire ? n_groups_wire * C : n_lines;
+        if (lines <= 0) continue;
+        CK(ctx, launch_pc_direct(wire, p, plan.taps.as<float2>(), (int)i, plan.segs[i].d.out_len, lines, st));
+        ctx->launches++;
+    }
+    return RB200_OK;
+}
+
+static void factor_radices(int P, int* radix, int* n) {
+    int k = 0, m = P;
+    while (m % 8 == 0) { radix[k++] = 8; m /= 8; }
+    while (m % 4 == 0) { radix[k++] = 4; m /= 4; }
+    while (m % 2 == 0) { radix[k++] = 2; m /= 2; }
+    for (int f = 3; m > 1 && k < 15; f += 2)
+        while (m % f == 0 && k < 15) { radix[k++] = f; m /= f; }
+    if (m > 1) radix[k++] = m;
+    if (k == 0) radix[k++] = 1;
+    *n = k;
+}
+
+static int get_mtd_plan(rb200_ctx* ctx, int P, double beta, MtdPlan** out) {
+    long long bkey;
+    memcpy(&bkey, &beta, sizeof bkey);
+    auto key = std::make_pair(P, bkey);
+    auto it = ctx->mtd_plans.find(key);
+    if (it != ctx->mtd_plans.end()) { *out = it->second; return RB200_OK; }
+    MtdPlan* mp = new MtdPlan();
+    mp->P = P;
+    mp->beta = beta;
+    std::vector<double> w = kaiser_window(P, beta);
+    std::vector<float> wf(P);
+    for (int i = 0; i < P; ++i) wf[i] = (float)w[i];
+    std::vector<float2> tw(P);
+    for (int m = 0; m < P; ++m) {
+        const double a = -2.0 * M_PI * m / P;
+        tw[m] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    factor_radices(P, mp->radix, &mp->n_stages);
+    cudaError_t e = mp->window.ensure(P * sizeof(float));
+    if (e == cudaSuccess) e = mp->tw.ensure(P * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mp->window.p, wf.data(), P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mp->tw.p, tw.data(), P * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        delete mp;
+        ctx->err = std::string("mtd plan: ") + cudaGetErrorString(e);
+        return RB200_ERR_CUDA;
+    }
+    ctx->mtd_plans[key] = mp;
+    *out = mp;
+    return RB200_OK;
+}
+
+// zero-velocity rows, 0-based inclusive; lo > hi when disabled.  MP/fun_0v_pressing.m:4-6.
+static int zero_v_rows(int P, int div, int* lo, int* hi) {
+    if (div <= 0) { *lo = 1; *hi = 0; return RB200_OK; }
+    const long z = mround(P / 2.0), h = mround((double)P / div);
+    const long a = z - h, b = z + h;            // 1-based inclusive
+    if (a < 1 || b > P) return RB200_ERR_INDEX;
+    *lo = (int)a - 1;
+    *hi = (int)b - 1;
+    return RB200_OK;
+}
+
+static int run_mtd(rb200_ctx* ctx, const float2* in, float* out, int P, int in_ld, int out_ld, int cols, int n_slabs,
+                   double beta, int zero_div, int mti_lag, cudaStream_t st) {
+    if (P < 1) return fail(ctx, RB200_ERR_ARG, "MTD: P < 1");
+    if (!mtd_has_fast_path(P) && P > mtd_generic_max_p()) return fail(ctx, RB200_ERR_UNSUPPORTED, "MTD: P beyond the generic kernel's shared-memory envelope (12288)");
+    MtdPlan* mp = nullptr;
+    int rc = get_mtd_plan(ctx, P, beta, &mp);
+    if (rc) return rc;
+    MtdParams p;
+    memset(&p, 0, sizeof p);
+    p.in = in;
+    p.out = out;
+    p.window = mp->window.as<float>();
+    p.tw = mp->tw.as<float2>();
+    p.P = P;
+    p.in_ld = in_ld;
+    p.out_ld = out_ld;
+    p.cols = cols;
+    p.mti_lag = mti_lag;
+    rc = zero_v_rows(P, zero_div, &p.zv_lo, &p.zv_hi);
+    if (rc) return fail(ctx, rc, "fun_0v_pressing: Index in position 1 is invalid");
+    p.n_stages = mp->n_stages;
+    for (int i = 0; i < mp->n_stages; ++i) p.radix[i] = mp->radix[i];
+    CK(ctx, launch_mtd(p, n_slabs, st));
+    ctx->launches++;
+    return RB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------
+extern "C" int rb200_version(void) { return RB200_VERSION_MAJOR * 100 + RB200_VERSION_MINOR; }
+
+static void default_config(rb200_config* c) {
+    memset(c, 0, sizeof *c);
+    c->struct_size = (int32_t)sizeof(rb200_config);
+    c->n_prt = 64;
+    c->n_range = 4096;
+    c->n_lanes = 16;
+    c->max_cpi = 1;
+    c->max_det = 65536;
+    c->zero_v_div = 150;
+    c->kaiser_beta = 8.0;
+    c->cfar_ref_r = c->cfar_ref_v = 5;
+    c->cfar_guard_r = c->cfar_guard_v = 7;
+    c->cfar_t_r = c->cfar_t_v = 5.0;
+    c->cfar_range_stage = 1;
+}
+
+static int validate_cfar(rb200_ctx* ctx, const rb200_config& c) {
+    if (c.cfar_ref_r < 1 || c.cfar_ref_v < 1 || c.cfar_guard_r < 0 || c.cfar_guard_v < 0)
+        return fail(ctx, RB200_ERR_ARG, "config: CFAR ref cells must be >= 1 and guard cells >= 0");
+    if ((c.cfar_method_r != 0 && c.cfar_method_r != 1) || (c.cfar_method_v != 0 && c.cfar_method_v != 1))
+        return fail(ctx, RB200_ERR_ARG, "config: CFAR method must be 0 (GO) or 1 (SO)");
+    return RB200_OK;
+}
+
+extern "C" int rb200_create(rb200_ctx** out, int device, const rb200_config* cfg) {
+    if (!out) { g_create_error = "rb200_create: out is NULL"; return RB200_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("rb200_create: no CUDA device (") + cudaGetErrorString(e) + "); libradar_b200 has no CPU fallback";
+        return RB200_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "rb200_create: device index out of range"; return RB200_ERR_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return RB200_ERR_CUDA; }
+    rb200_ctx* c = new rb200_ctx();
+    c->device = device;
+    default_config(&c->cfg);
+    if (cfg) {
+        if (cfg->struct_size != (int32_t)sizeof(rb200_config)) { delete c; g_create_error = "rb200_create: rb200_config.struct_size mismatch"; return RB200_ERR_ARG; }
+        c->cfg = *cfg;
+    }
+    const rb200_config& k = c->cfg;
+    if (k.n_prt < 1 || k.n_range < 1 || k.n_lanes < 1 || k.n_lanes > 255 || k.max_cpi < 1 || k.max_det < 1 || k.n_prt > 65535) {
+        delete c;
+        g_create_error = "rb200_create: geometry out of range (n_prt 1..65535, n_lanes 1..255, sizes >= 1)";
+        return RB200_ERR_ARG;
+    }
+    if (validate_cfar(c, k)) { g_create_error = c->err; delete c; return RB200_ERR_ARG; }
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = c->counters.ensure(4 * sizeof(int));
+    if (e == cudaSuccess) e = c->errflag.ensure(sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_counts, 4 * sizeof(int));
+    if (e != cudaSuccess) {
+        g_create_error = std::string("rb200_create: ") + cudaGetErrorString(e);
+        rb200_destroy(c);
+        return RB200_ERR_CUDA;
+    }
+    *out = c;
+    return RB200_OK;
+}
+
+extern "C" int rb200_destroy(rb200_ctx* c) {
+    if (!c) return RB200_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->plan.release();
+    for (auto& kv : c->mtd_plans) {
+        kv.second->window.release();
+        kv.second->tw.release();
+        delete kv.second;
+    }
+    DevBuf* bufs[] = {&c->gain, &c->raw, &c->pc, &c->rdm, &c->dets_v, &c->dets_2d, &c->counters, &c->vmask, &c->errflag,
+                      &c->s_in_re, &c->s_in_im, &c->s_a, &c->s_b, &c->s_c, &c->s_out_re, &c->s_out_im, &c->s_u8a, &c->s_u8b, &c->s_idx};
+    for (DevBuf* b : bufs) b->release();
+    if (c->h_dets) cudaFreeHost(c->h_dets);
+    if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RB200_OK;
+}
+
+extern "C" const char* rb200_last_error(const rb200_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int rb200_get_config(const rb200_ctx* c, rb200_config* out) {
+    if (!c || !out) return RB200_ERR_ARG;
+    *out = c->cfg;
+    return RB200_OK;
+}
+
+extern "C" int rb200_set_cfar(rb200_ctx* c, const rb200_config* cfg) {
+    if (!c || !cfg) return RB200_ERR_ARG;
+    rb200_config n = c->cfg;
+    n.cfar_ref_r = cfg->cfar_ref_r; n.cfar_guard_r = cfg->cfar_guard_r; n.cfar_method_r = cfg->cfar_method_r;
+    n.cfar_ref_v = cfg->cfar_ref_v; n.cfar_guard_v = cfg->cfar_guard_v; n.cfar_method_v = cfg->cfar_method_v;
+    n.cfar_t_r = cfg->cfar_t_r; n.cfar_t_v = cfg->cfar_t_v; n.cfar_n0 = cfg->cfar_n0; n.cfar_range_stage = cfg->cfar_range_stage;
+    int rc = validate_cfar(c, n);
+    if (rc) return rc;
+    c->cfg = n;
+    return RB200_OK;
+}
+
+extern "C" int rb200_set_waveform(rb200_ctx* c, const rb200_segment* segs, int nseg) {
+    if (!c) return RB200_ERR_ARG;
+    cudaSetDevice(c->device);
+    return build_plan(c, c->plan, segs, nseg);
+}
+
+extern "C" int rb200_set_stc(rb200_ctx* c, const double* stc_db, int n) {
+    if (!c || n < 0 || (n > 0 && !stc_db)) return RB200_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (n == 0) { c->gain_n = 0; return RB200_OK; }
+    const int R = c->cfg.n_range;
+    if (n > R) return fail(c, RB200_ERR_DIM_MISMATCH, "fun_iSTC: STC curve longer than the PRT (arrays have incompatible sizes)");
+    std::vector<float> g(R, 1.0f);
+    for (int i = 0; i < n; ++i) g[i] = (float)std::pow(10.0, stc_db[i] / 20.0);
+    CK(c, c->gain.ensure(R * sizeof(float)));
+    CK(c, cudaMemcpyAsync(c->gain.p, g.data(), R * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->gain_n = n;
+    return RB200_OK;
+}
+
+extern "C" int rb200_set_dbf(rb200_ctx* c, const double* w_re, const double* w_im, int n_beams) {
+    if (!c) return RB200_ERR_ARG;
+    if (n_beams == 0) return RB200_OK;
+    (void)w_re; (void)w_im;
+    return fail(c, RB200_ERR_UNSUPPORTED, "rb200_set_dbf: DBF weighting (SURVEY 8f row f1) is not implemented in this build");
+}
+
+// ---------------------------------------------------------------------------------------------
+// MATLAB-layout entry points
+// ---------------------------------------------------------------------------------------------
+static int upload_z(rb200_ctx* c, const double* re, const double* im, size_t n, const double** dre, const double** dim) {
+    CK(c, c->s_in_re.ensure(std::max<size_t>(n, 1) * sizeof(double)));
+    CK(c, cudaMemcpyAsync(c->s_in_re.p, re, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    *dre = c->s_in_re.as<double>();
+    *dim = nullptr;
+    if (im) {
+        CK(c, c->s_in_im.ensure(std::max<size_t>(n, 1) * sizeof(double)));
+        CK(c, cudaMemcpyAsync(c->s_in_im.p, im, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        *dim = c->s_in_im.as<double>();
+    }
+    return RB200_OK;
+}
+
+extern "C" int rb200_pulse_compression_z(rb200_ctx* c, const double* s0_re, const double* s0_im, int L,
+                                         const double* echo_re, const double* echo_im, int M, double* out_re, double* out_im) {
+    if (!c || !s0_re || L < 1 || M < 0 || (M > 0 && !echo_re) || !out_re || !out_im) return fail(c, RB200_ERR_ARG, "pulse_compression: bad argument");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    const int N = L + M - 1;
+    if (N < 1) return RB200_OK;
+    if (M == 0) {   // fft of an empty vector padded to N is zero -> output zeros(1,N); device memset, no CPU maths
+        CK(c, c->s_out_re.ensure(N * sizeof(double)));
+        CK(c, cudaMemsetAsync(c->s_out_re.p, 0, N * sizeof(double), c->stream));
+        CK(c, cudaMemcpyAsync(out_re, c->s_out_re.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemcpyAsync(out_im, c->s_out_re.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        return RB200_OK;
+    }
+    // full convolution with conj(flip(s0)): y[m] = sum_j x[m-(L-1)+j] conj(s0[j])  (MP/fun_pulse_compression.m:4,19-22)
+    Plan tmp;
+    rb200_segment s;
+    memset(&s, 0, sizeof s);
+    s.in_start = 0; s.in_len = M; s.out_start = 0; s.out_len = N;
+    s.kind = RB200_SEG_MF; s.align = RB200_ALIGN_LEADING_EDGE;
+    s.n_taps = L; s.taps_re = s0_re; s.taps_im = s0_im; s.scale = 1.0;
+    int rc = build_plan(c, tmp, &s, 1);
+    if (rc) { tmp.release(); return rc; }
+    tmp.segs[0].d.pre = L - 1;
+    const double *dre, *dim;
+    rc = upload_z(c, echo_re, echo_im, M, &dre, &dim);
+    if (rc) { tmp.release(); return rc; }
+    cudaError_t e = c->s_a.ensure((size_t)M * sizeof(float2));
+    if (e == cudaSuccess) e = c->s_b.ensure((size_t)N * sizeof(float2));
+    if (e == cudaSuccess) e = c->s_out_re.ensure(N * sizeof(double));
+    if (e == cudaSuccess) e = c->s_out_im.ensure(N * sizeof(double));
+    if (e == cudaSuccess) e = launch_z_to_planar(dre, dim, c->s_a.as<float2>(), 1, M, c->stream);
+    if (e != cudaSuccess) { tmp.release(); c->err = cudaGetErrorString(e); return RB200_ERR_CUDA; }
+    c->launches++;
+    rc = run_pc(c, tmp, false, c->s_a.p, c->s_b.as<float2>(), M, N, 1, 1, 0, 1, nullptr, c->stream);
+    if (!rc) {
+        e = launch_planar_to_z(c->s_b.as<float2>(), c->s_out_re.as<double>(), c->s_out_im.as<double>(), 1, N, c->stream);
+        c->launches++;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_re, c->s_out_re.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_im, c->s_out_im.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = RB200_ERR_CUDA; }
+    }
+    cudaStreamSynchronize(c->stream);
+    tmp.release();
+    return rc;
+}
+
+extern "C" int rb200_lss_pulse_compression_z(rb200_ctx* c, const double* echo_re, const double* echo_im, int P, int R,
+                                             double* out_re, double* out_im) {
+    if (!c || !echo_re || P < 1 || R < 1 || !out_re || !out_im) return fail(c, RB200_ERR_ARG, "lss_pulse_compression: bad argument");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    const size_t n = (size_t)P * R;
+    const double *dre, *dim;
+    int rc = upload_z(c, echo_re, echo_im, n, &dre, &dim);
+    if (rc) return rc;
+    CK(c, c->s_a.ensure(n * sizeof(float2)));
+    CK(c, c->s_b.ensure(n * sizeof(float2)));
+    CK(c, c->s_out_re.ensure(n * sizeof(double)));
+    CK(c, c->s_out_im.ensure(n * sizeof(double)));
+    CK(c, launch_z_to_planar(dre, dim, c->s_a.as<float2>(), P, R, c->stream));
+    c->launches++;
+    rc = run_pc(c, c->plan, false, c->s_a.p, c->s_b.as<float2>(), R, R, 1, 1, 0, P, nullptr, c->stream);
+    if (rc) return rc;
+    CK(c, launch_planar_to_z(c->s_b.as<float2>(), c->s_out_re.as<double>(), c->s_out_im.as<double>(), P, R, c->stream));
+    c->launches++;
+    CK(c, cudaMemcpyAsync(out_re, c->s_out_re.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(out_im, c->s_out_im.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RB200_OK;
+}
+
+extern "C" int rb200_process_mtd_z(rb200_ctx* c, const double* re, const double* im, int rows, int cols, int len_prt, int num_prt,
+                                   double beta, double* out) {
+    if (!c || !re || rows < 1 || cols < 0 || len_prt < 0 || num_prt < 1 || !out) return fail(c, RB200_ERR_ARG, "process_mtd: bad argument");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    if (rows != num_prt) {
+        if (rows == 1 || num_prt == 1) return fail(c, RB200_ERR_UNSUPPORTED, "process_mtd: implicit expansion (rows==1 or Num_PRTperFrame==1) is not supported");
+        return fail(c, RB200_ERR_DIM_MISMATCH, "fun_Process_MTD: arrays have incompatible sizes (rows of ProSignal != Num_PRTperFrame)");
+    }
+    if (len_prt > cols) return fail(c, RB200_ERR_INDEX, "fun_Process_MTD: Index in position 2 exceeds array bounds (Len_PRT > columns)");
+    if (len_prt == 0) return RB200_OK;
+    const int P = rows;
+    const size_t n = (size_t)P * cols, no = (size_t)P * len_prt;
+    const double *dre, *dim;
+    int rc = upload_z(c, re, im, n, &dre, &dim);
+    if (rc) return rc;
+    CK(c, c->s_a.ensure(n * sizeof(float2)));
+    CK(c, c->s_c.ensure(no * sizeof(float)));
+    CK(c, c->s_out_re.ensure(no * sizeof(double)));
+    CK(c, launch_z_to_planar(dre, dim, c->s_a.as<float2>(), P, cols, c->stream));
+    c->launches++;
+    rc = run_mtd(c, c->s_a.as<float2>(), c->s_c.as<float>(), P, cols, len_prt, len_prt, 1, beta, 0, 0, c->stream);
+    if (rc) return rc;
+    CK(c, launch_f32_rowmajor_to_d_colmajor(c->s_c.as<float>(), c->s_out_re.as<double>(), P, len_prt, c->stream));
+    c->launches++;
+    CK(c, cudaMemcpyAsync(out, c->s_out_re.p, no * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RB200_OK;
+}
+
+extern "C" int rb200_zero_v_pressing_d(rb200_ctx* c, const double* mtd, int P, int R, int div, double* out) {
+    if (!c || !mtd || !out || P < 1 || R < 0 || div < 1) return fail(c, RB200_ERR_ARG, "zero_v_pressing: bad argument");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    int lo, hi;
+    if (zero_v_rows(P, div, &lo, &hi)) return fail(c, RB200_ERR_INDEX, "fun_0v_pressing: Index in position 1 is invalid");
+    const size_t n = (size_t)P * R;
+    if (n == 0) return RB200_OK;
+    CK(c, c->s_in_re.ensure(n * sizeof(double)));
+    CK(c, c->s_out_re.ensure(n * sizeof(double)));
+    CK(c, cudaMemcpyAsync(c->s_in_re.p, mtd, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(c, launch_zero_rows_d_colmajor(c->s_in_re.as<double>(), c->s_out_re.as<double>(), P, R, lo, hi, c->stream));
+    c->launches++;
+    CK(c, cudaMemcpyAsync(out, c->s_out_re.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RB200_OK;
+}
+
+extern "C" int rb200_mtd_produce_z(rb200_ctx* c, const double* echo_re, const double* echo_im, int P, int R, double beta,
+                                   int zero_v_div, double* out) {
+    if (!c || !echo_re || P < 1 || R < 1 || !out) return fail(c, RB200_ERR_ARG, "mtd_produce: bad argument");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    const size_t n = (size_t)P * R;
+    const double *dre, *dim;
+    int rc = upload_z(c, echo_re, echo_im, n, &dre, &dim);
+    if (rc) return rc;
+    CK(c, c->s_a.ensure(n * sizeof(float2)));
+    CK(c, c->s_b.ensure(n * sizeof(float2)));
+    CK(c, c->s_c.ensure(n * sizeof(float)));
+    CK(c, c->s_out_re.ensure(n * sizeof(double)));
+    CK(c, launch_z_to_planar(dre, dim, c->s_a.as<float2>(), P, R, c->stream));
+    c->launches++;
+    rc = run_pc(c, c->plan, false, c->s_a.p, c->s_b.as<float2>(), R, R, 1, 1, 0, P, nullptr, c->stream);
+    if (rc) return rc;
+    rc = run_mtd(c, c->s_b.as<float2>(), c->s_c.as<float>(), P, R, R, R, 1, beta, zero_v_div, c->cfg.mti_lag, c->stream);
+    if (rc) return rc;
+    CK(c, launch_f32_rowmajor_to_d_colmajor(c->s_c.as<float>(), c->s_out_re.as<double>(), P, R, c->stream));
+    c->launches++;
+    CK(c, cudaMemcpyAsync(out, c->s_out_re.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RB200_OK;
+}
+
+static int fetch_errflag(rb200_ctx* c, const char* what) {
+    CK(c, cudaMemcpyAsync(c->h_counts + 3, c->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (c->h_counts[3]) return fail(c, RB200_ERR_INDEX, what);
+    return RB200_OK;
+}
+
+extern "C" int rb200_cfar1d_sub_d(rb200_ctx* c, const double* data, int rows, int cols, int ref, int guard, double T, int method,
+                                  double* out) {
+    return rb200_cfar1d_fix_d(c, data, rows, cols, ref, guard, T, method, nullptr, 0, nullptr, 0, out);
+}
+
+extern "C" int rb200_cfar1d_fix_d(rb200_ctx* c, const double* data, int rows, int cols, int ref, int guard, double T, int method,
+                                  const int32_t* rows_fix, int n_rows_fix, const int32_t* cols_fix, int n_cols_fix, double* out) {
+    if (!c || !data || !out || rows < 0 || cols < 0 || ref < 1 || guard < 0 || (method != 0 && method != 1) || n_rows_fix < 0 || n_cols_fix < 0)
+        return fail(c, RB200_ERR_ARG, "cfar1d: bad argument");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    const size_t n = (size_t)rows * cols;
+    if (n == 0) return RB200_OK;
+    for (int i = 0; rows_fix && i < n_rows_fix; ++i)
+        if (rows_fix[i] < 1 || rows_fix[i] > rows) return fail(c, RB200_ERR_INDEX, "Function_CFAR1D_sub_fixCells: row index exceeds array bounds");
+    for (int i = 0; cols_fix && i < n_cols_fix; ++i)
+        if (cols_fix[i] < 1 || cols_fix[i] > cols) return fail(c, RB200_ERR_INDEX, "Function_CFAR1D_sub_fixCells: column index exceeds array bounds");
+    CK(c, c->s_in_re.ensure(n * sizeof(double)));
+    CK(c, c->s_u8a.ensure(n));
+    CK(c, c->s_out_re.ensure(n * sizeof(double)));
+    CK(c, cudaMemcpyAsync(c->s_in_re.p, data, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemsetAsync(c->s_u8a.p, 0, n, c->stream));
+    CK(c, cudaMemsetAsync(c->errflag.p, 0, sizeof(int), c->stream));
+    const int* d_rows = nullptr;
+    const int* d_cols = nullptr;
+    if (rows_fix || cols_fix) {
+        CK(c, c->s_idx.ensure((size_t)(n_rows_fix + n_cols_fix + 1) * sizeof(int)));
+        if (rows_fix) {
+            CK(c, cudaMemcpyAsync(c->s_idx.p, rows_fix, n_rows_fix * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            d_rows = c->s_idx.as<int>();
+        }
+        if (cols_fix) {
+            CK(c, cudaMemcpyAsync(c->s_idx.as<int>() + n_rows_fix, cols_fix, n_cols_fix * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            d_cols = c->s_idx.as<int>() + n_rows_fix;
+        }
+    }
+    CK(c, launch_cfar1d_f64(c->s_in_re.as<double>(), rows, cols, ref, guard, T, method, d_rows, n_rows_fix, d_cols, n_cols_fix,
+                            c->s_u8a.as<uint8_t>(), c->errflag.as<int>(), c->stream));
+    c->launches++;
+    CK(c, launch_u8_to_d(c->s_u8a.as<uint8_t>(), c->s_out_re.as<double>(), n, c->stream));
+    c->launches++;
+    CK(c, cudaMemcpyAsync(out, c->s_out_re.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return fetch_errflag(c, "Function_CFAR1D_sub: Index exceeds array bounds (axis shorter than 2*(ref+guard))");
+}
+
+extern "C" int rb200_execute_cfar_d(rb200_ctx* c, const double* mtd, int V, int R, int ref_r, int guard_r, double t_r, int method_r,
+                                    int ref_v, int guard_v, double t_v, int method_v, int n0, int range_stage,
+                                    double* out_flag, double* out_flag_v) {
+    if (!c || !mtd || !out_flag || V < 1 || R < 1 || ref_r < 1 || ref_v < 1 || guard_r < 0 || guard_v < 0 ||
+        (method_r != 0 && method_r != 1) || (method_v != 0 && method_v != 1))
+        return fail(c, RB200_ERR_ARG, "execute_cfar: bad argument");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    // rows n0+2 .. V-n0 (1-based) -> [n0+1, V-n0) 0-based   (CW/executeCFAR.m:23)
+    if (n0 < -1 || n0 + 2 < 1 || V - n0 > V) return fail(c, RB200_ERR_INDEX, "executeCFAR: Index in position 1 exceeds array bounds");
+    const size_t n = (size_t)V * R;
+    CfarParams p;
+    memset(&p, 0, sizeof p);
+    p.V = V; p.R = R;
+    p.v_lo = n0 + 1; p.v_hi = V - n0;
+    p.ref_r = ref_r; p.guard_r = guard_r; p.meth_r = method_r;
+    p.ref_v = ref_v; p.guard_v = guard_v; p.meth_v = method_v;
+    p.range_stage = range_stage ? 1 : 0;
+    p.max_det = (int)std::min<size_t>(n, (size_t)1 << 30);
+    p.n_lanes = 1; p.cpi0 = 0;
+    const int Rw = (R + 31) / 32;
+    CK(c, c->s_in_re.ensure(n * sizeof(double)));
+    CK(c, c->s_u8a.ensure(n));
+    CK(c, c->s_u8b.ensure(n));
+    CK(c, c->s_out_re.ensure(n * sizeof(double)));
+    CK(c, c->s_a.ensure(n * sizeof(rb200_det)));
+    CK(c, c->s_b.ensure((size_t)V * Rw * sizeof(uint32_t)));
+    CK(c, cudaMemcpyAsync(c->s_in_re.p, mtd, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemsetAsync(c->s_u8a.p, 0, n, c->stream));
+    CK(c, cudaMemsetAsync(c->s_u8b.p, 0, n, c->stream));
+    CK(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(int), c->stream));
+    CK(c, cudaMemsetAsync(c->errflag.p, 0, sizeof(int), c->stream));
+    if (p.v_hi > p.v_lo) {
+        CK(c, launch_cfar_f64_colmajor(c->s_in_re.as<double>(), p, t_r, t_v, c->s_a.p, c->counters.as<int>(),
+                                       c->s_b.as<uint32_t>(), c->s_u8a.as<uint8_t>(), c->s_u8b.as<uint8_t>(), c->errflag.as<int>(), c->stream));
+        c->launches += range_stage ? 2 : 1;
+    }
+    // rCFARDetect_Flag == 0: cfarResultFlag_Matrix = cfarResultFlag_MatrixV (executeCFAR.m:91)
+    const uint8_t* final_flags = range_stage ? c->s_u8a.as<uint8_t>() : c->s_u8b.as<uint8_t>();
+    CK(c, launch_u8_to_d(final_flags, c->s_out_re.as<double>(), n, c->stream));
+    c->launches++;
+    CK(c, cudaMemcpyAsync(out_flag, c->s_out_re.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (out_flag_v) {
+        CK(c, c->s_out_im.ensure(n * sizeof(double)));
+        CK(c, launch_u8_to_d(c->s_u8b.as<uint8_t>(), c->s_out_im.as<double>(), n, c->stream));
+        c->launches++;
+        CK(c, cudaMemcpyAsync(out_flag_v, c->s_out_im.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    return fetch_errflag(c, "executeCFAR: Index exceeds array bounds (CFAR axis shorter than 2*(ref+guard))");
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched wire-format entry points
+// ---------------------------------------------------------------------------------------------
+static bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+extern "C" int rb200_unpack_ddc_i16(rb200_ctx* c, const int16_t* raw, int n_cpi, float* out_ri) {
+    if (!c || !raw || !out_ri || n_cpi < 1) return fail(c, RB200_ERR_ARG, "unpack: bad argument");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    const rb200_config& k = c->cfg;
+    const size_t cells = (size_t)n_cpi * k.n_prt * k.n_range * k.n_lanes;
+    CK(c, c->raw.ensure(cells * 4));
+    CK(c, c->s_a.ensure(cells * sizeof(float2)));
+    CK(c, cudaMemcpyAsync(c->raw.p, raw, cells * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, launch_unpack(c->raw.as<int16_t>(), c->s_a.as<float2>(), n_cpi * k.n_prt, k.n_prt, k.n_range, k.n_lanes, c->stream));
+    c->launches++;
+    CK(c, cudaMemcpyAsync(out_ri, c->s_a.p, cells * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RB200_OK;
+}
+
+static int chunk_size(const rb200_ctx* c) {
+    const char* env = getenv("RB200_CHUNK");
+    int g = env ? atoi(env) : c->cfg.chunk_cpi;
+    if (g <= 0) {
+        // default: keep raw + PC + RDM of one chunk inside ~96 MB of the 126 MB L2
+        const double per_cpi = (double)c->cfg.n_prt * c->cfg.n_range * c->cfg.n_lanes * 16.0;
+        g = (int)std::floor(96e6 / per_cpi);
+    }
+    return std::max(1, std::min(g, c->cfg.max_cpi));
+}
+
+static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float* rdm_dev, cudaStream_t st) {
+    const rb200_config& k = c->cfg;
+    const int P = k.n_prt, R = k.n_range, C = k.n_lanes;
+    if (n_cpi < 1 || n_cpi > k.max_cpi) return fail(c, RB200_ERR_ARG, "chain: n_cpi must be in 1..max_cpi");
+    if (k.cfar_n0 < 0) return fail(c, RB200_ERR_INDEX, "executeCFAR: Index in position 1 exceeds array bounds (MTD_0_num < 0)");
+    const int G = chunk_size(c);
+    const size_t cpi_cells = (size_t)P * R * C;
+    const int Rw = (R + 31) / 32;
+    CK(c, c->pc.ensure((size_t)G * cpi_cells * sizeof(float2)));
+    CK(c, c->dets_v.ensure((size_t)k.max_det * sizeof(rb200_det)));
+    CK(c, c->dets_2d.ensure((size_t)k.max_det * sizeof(rb200_det)));
+    CK(c, c->vmask.ensure((size_t)G * C * P * Rw * sizeof(uint32_t)));
+    float* rdm_base = rdm_dev;
+    if (!rdm_base) {
+        CK(c, c->rdm.ensure((size_t)G * cpi_cells * sizeof(float)));
+        rdm_base = c->rdm.as<float>();
+    }
+    CfarParams cp;
+    memset(&cp, 0, sizeof cp);
+    cp.V = P; cp.R = R;
+    cp.v_lo = k.cfar_n0 + 1; cp.v_hi = P - k.cfar_n0;
+    cp.ref_r = k.cfar_ref_r; cp.guard_r = k.cfar_guard_r; cp.meth_r = k.cfar_method_r;
+    cp.ref_v = k.cfar_ref_v; cp.guard_v = k.cfar_guard_v; cp.meth_v = k.cfar_method_v;
+    cp.range_stage = k.cfar_range_stage ? 1 : 0;
+    cp.max_det = k.max_det;
+    cp.n_lanes = C;
+    c->launches = 0;
+    CK(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(int), st));
+    CK(c, cudaMemsetAsync(c->errflag.p, 0, sizeof(int), st));
+    CK(c, cudaEventRecord(c->ev0, st));
+    for (int c0 = 0; c0 < n_cpi; c0 += G) {
+        const int g = std::min(G, n_cpi - c0);
+        const int16_t* raw_chunk = raw_dev + (size_t)c0 * cpi_cells * 2;
+        float* rdm_chunk = rdm_dev ? rdm_base + (size_t)c0 * cpi_cells : rdm_base;
+        int rc = run_pc(c, c->plan, true, raw_chunk, c->pc.as<float2>(), R, R, C, P, g * P, 0,
+                        c->gain_n ? c->gain.as<float>() : nullptr, st);
+        if (rc) return rc;
+        rc = run_mtd(c, c->pc.as<float2>(), rdm_chunk, P, R, R, R, g * C, k.kaiser_beta, k.zero_v_div, k.mti_lag, st);
+        if (rc) return rc;
+        cp.cpi0 = c0;
+        if (cp.v_hi > cp.v_lo) {
+            // hits of this chunk start where the list currently ends
+            CK(c, cudaMemcpyAsync(c->counters.as<int>() + 2, c->counters.as<int>() + 0, sizeof(int), cudaMemcpyDeviceToDevice, st));
+            CK(c, launch_cfar_f32(rdm_chunk, cp, (float)k.cfar_t_r, (float)k.cfar_t_v, g * C, c->dets_v.p, c->counters.as<int>() + 0,
+                                  c->dets_2d.p, c->counters.as<int>() + 1, c->vmask.as<uint32_t>(), nullptr, nullptr,
+                                  c->errflag.as<int>(), st));
+            c->launches += cp.range_stage ? 2 : 1;
+        }
+        c->last_chunk_cpis = g;
+    }
+    CK(c, cudaEventRecord(c->ev1, st));
+    c->have_timing = true;
+    return RB200_OK;
+}
+
+extern "C" int rb200_chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float* rdm_dev, void* stream) {
+    if (!c || !raw_dev) return fail(c, RB200_ERR_ARG, "chain_enqueue: bad argument");
+    cudaSetDevice(c->device);
+    return chain_enqueue(c, raw_dev, n_cpi, rdm_dev, stream ? (cudaStream_t)stream : c->stream);
+}
+
+static int chain_fetch(rb200_ctx* c, rb200_det* dets, bool dets_on_device, int* n_det, cudaStream_t st) {
+    const int cap = c->cfg.max_det;
+    CK(c, cudaMemcpyAsync(c->h_counts, c->counters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(c->h_counts + 3, c->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    const int nv = c->h_counts[0], n2 = c->cfg.cfar_range_stage ? c->h_counts[1] : 0;
+    if (n_det) *n_det = nv + n2;
+    if (c->h_counts[3]) return fail(c, RB200_ERR_INDEX, "executeCFAR: Index exceeds array bounds (CFAR axis shorter than 2*(ref+guard))");
+    if (dets) {
+        // 2-D records first (the product), then velocity-stage records; at most max_det in total
+        const int k2 = std::min(n2, cap);
+        const int kv = std::min(std::min(nv, cap), cap - k2);
+        const cudaMemcpyKind kind = dets_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        if (k2) CK(c, cudaMemcpyAsync(dets, c->dets_2d.p, (size_t)k2 * sizeof(rb200_det), kind, st));
+        if (kv) CK(c, cudaMemcpyAsync(dets + k2, c->dets_v.p, (size_t)kv * sizeof(rb200_det), kind, st));
+        CK(c, cudaStreamSynchronize(st));
+    }
+    if (nv > cap || nv + n2 > cap) return fail(c, RB200_ERR_OVERFLOW, "detection list truncated: raise rb200_config.max_det");
+    return RB200_OK;
+}
+
+extern "C" int rb200_chain_fetch(rb200_ctx* c, rb200_det* dets_host, int* n_det) {
+    if (!c) return RB200_ERR_ARG;
+    cudaSetDevice(c->device);
+    return chain_fetch(c, dets_host, dets_host && is_device_ptr(dets_host), n_det, c->stream);
+}
+
+extern "C" int rb200_chain_i16(rb200_ctx* c, const int16_t* raw, int n_cpi, float* rdm_out, rb200_det* dets, int* n_det, void* stream) {
+    if (!c || !raw) return fail(c, RB200_ERR_ARG, "chain: bad argument");
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const rb200_config& k = c->cfg;
+    if (n_cpi < 1 || n_cpi > k.max_cpi) return fail(c, RB200_ERR_ARG, "chain: n_cpi must be in 1..max_cpi");
+    const size_t cpi_cells = (size_t)k.n_prt * k.n_range * k.n_lanes;
+    const int16_t* raw_dev = raw;
+    if (!is_device_ptr(raw)) {
+        CK(c, c->raw.ensure((size_t)n_cpi * cpi_cells * 4));
+        CK(c, cudaMemcpyAsync(c->raw.p, raw, (size_t)n_cpi * cpi_cells * 4, cudaMemcpyHostToDevice, st));
+        raw_dev = c->raw.as<int16_t>();
+    }
+    float* rdm_dev = nullptr;
+    bool rdm_to_host = false;
+    if (rdm_out) {
+        if (is_device_ptr(rdm_out)) rdm_dev = rdm_out;
+        else {
+            CK(c, c->rdm.ensure((size_t)std::max(n_cpi, chunk_size(c)) * cpi_cells * sizeof(float)));
+            rdm_dev = c->rdm.as<float>();
+            rdm_to_host = true;
+        }
+    }
+    int rc = chain_enqueue(c, raw_dev, n_cpi, rdm_dev, st);
+    if (rc) return rc;
+    if (rdm_to_host) CK(c, cudaMemcpyAsync(rdm_out, rdm_dev, (size_t)n_cpi * cpi_cells * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return chain_fetch(c, dets, dets && is_device_ptr(dets), n_det, st);
+}
+
+extern "C" int rb200_debug_fetch_pc(rb200_ctx* c, int cpi_in_chunk, float* out_ri) {
+    if (!c || !out_ri || cpi_in_chunk < 0 || cpi_in_chunk >= c->last_chunk_cpis) return fail(c, RB200_ERR_ARG, "debug_fetch_pc: bad argument");
+    cudaSetDevice(c->device);
+    const size_t cpi_cells = (size_t)c->cfg.n_prt * c->cfg.n_range * c->cfg.n_lanes;
+    CK(c, cudaMemcpy(out_ri, c->pc.as<float2>() + (size_t)cpi_in_chunk * cpi_cells, cpi_cells * sizeof(float2), cudaMemcpyDeviceToHost));
+    return RB200_OK;
+}
+
+extern "C" int rb200_last_device_ms(const rb200_ctx* c, float* ms) {
+    if (!c || !ms || !c->have_timing) return RB200_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return RB200_ERR_CUDA;
+    return cudaEventElapsedTime(ms, c->ev0, c->ev1) == cudaSuccess ? RB200_OK : RB200_ERR_CUDA;
+}
+
+extern "C" int rb200_last_launch_count(const rb200_ctx* c, int* n) {
+    if (!c || !n) return RB200_ERR_ARG;
+    *n = c->launches;
+    return RB200_OK;
+}

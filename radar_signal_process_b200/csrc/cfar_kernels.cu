@@ -1,0 +1,211 @@
+// cfar_kernels.cu -- K3: 2-D CA-CFAR (velocity axis dense, range axis on +-1 cells around velocity hits)
+//                     with warp-ballot detection compaction.
+//
+// Replaces CW/executeCFAR.m:21-92, CW/Function_CFAR1D_sub.m:17-69 and
+// CW/Function_CFAR1D_sub_fixCells.m:23-87.
+//
+//   stage V  (executeCFAR.m:28): every cell of the tested rows [n0+1, V-n0) is compared with
+//            T_V * GO/SO(mean(left window), mean(right window)) along velocity; a window that falls
+//            off the (cropped) axis is replaced by the other one (Function_CFAR1D_sub.m:30-39);
+//            the compare is >= (:46).  Hits are compacted with __ballot_sync + one atomic per warp
+//            into the detection list (kind = RB200_DET_V) and into a 1-bit-per-cell mask.
+//   stage R  (executeCFAR.m:45-75): one thread per velocity hit (v,r) tests the range cells
+//            {r-1,r,r+1} on row v and elects the first maximum among the passing ones (:64-73).
+//            Because every write of the serial loop is "set to 1" the result is order independent;
+//            the thread emits the elected cell (kind = RB200_DET_2D) unless a hit with a smaller
+//            column elects the same cell (deterministic de-duplication through the bit mask).
+//
+// The same templates serve the float chain (row-major [v][r], list output) and the MATLAB-layout
+// double entry points (column-major, dense 0/1 outputs, sums accumulated left-to-right so flags are
+// bit-identical to the double-precision M-code).
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/radar_b200.h"
+
+namespace rb {
+
+// One CA-CFAR decision for element y of an axis of length N whose element i sits at base[i*stride].
+template <typename T>
+__device__ __forceinline__ bool cfar_decide(const T* __restrict__ base, ptrdiff_t stride, int y, int N, int ref, int guard,
+                                            T thr, int method, int* err_flag) {
+    const int l1 = y - guard - ref;
+    const int r1 = y + guard + 1;
+    const bool okL = l1 >= 0;
+    const bool okR = (y + guard + ref) <= N - 1;
+    if (!okL && !okR) {            // MATLAB: index exceeds array bounds
+        if (err_flag) *err_flag = 1;
+        return false;
+    }
+    T sl = 0, sr = 0;
+    if (okL) for (int j = 0; j < ref; ++j) sl += base[(ptrdiff_t)(l1 + j) * stride];
+    if (okR) for (int j = 0; j < ref; ++j) sr += base[(ptrdiff_t)(r1 + j) * stride];
+    const T mr = sr / (T)ref, ml = sl / (T)ref;
+    const T a = okL ? ml : mr;
+    const T b = okR ? mr : ml;
+    const T mu = method == 0 ? (a > b ? a : b) : (a < b ? a : b);
+    return base[(ptrdiff_t)y * stride] >= mu * thr;
+}
+
+// Stage V.  Thread <-> one cell; 32 consecutive threads share a row (row-major) so the ballot word is
+// one mask word.  ROWMAJOR: element (v,r) at v*R + r (float chain).  Otherwise column-major v + V*r.
+template <typename T, bool ROWMAJOR>
+__global__ void cfar_v_kernel(const T* __restrict__ rdm, const CfarParams p, T t_v, int n_slabs,
+                              rb200_det* __restrict__ dets, int* __restrict__ det_count,
+                              uint32_t* __restrict__ vmask, uint8_t* __restrict__ flagv, int* err_flag) {
+    const int Rw = (p.R + 31) / 32;
+    const int nv = p.v_hi - p.v_lo;
+    const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    const int lane = threadIdx.x & 31;
+    const size_t total_words = (size_t)n_slabs * nv * Rw;
+    if (warp_global >= total_words) return;
+    const int word = (int)(warp_global % Rw);
+    const size_t t1 = warp_global / Rw;
+    const int vi = (int)(t1 % nv);
+    const int slab = (int)(t1 / nv);
+    const int r = word * 32 + lane;
+    const int v = p.v_lo + vi;
+    bool hit = false;
+    T amp = 0;
+    if (r < p.R) {
+        const T* slab_base = rdm + (size_t)slab * p.V * p.R;
+        const T* col = ROWMAJOR ? slab_base + (size_t)p.v_lo * p.R + r : slab_base + p.v_lo + (size_t)p.V * r;
+        const ptrdiff_t sv = ROWMAJOR ? p.R : 1;
+        hit = cfar_decide<T>(col, sv, vi, nv, p.ref_v, p.guard_v, t_v, p.meth_v, err_flag);
+        if (hit) amp = col[(ptrdiff_t)vi * sv];
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) vmask[((size_t)slab * p.V + v) * Rw + word] = ball;
+    if (flagv && hit) flagv[ROWMAJOR ? ((size_t)slab * p.V + v) * p.R + r : (size_t)slab * p.V * p.R + v + (size_t)p.V * r] = 1;
+    if (ball == 0) return;
+    int basei = 0;
+    if (lane == 0) basei = atomicAdd(det_count, __popc(ball));
+    basei = __shfl_sync(0xffffffffu, basei, 0);
+    if (hit) {
+        const int slot = basei + __popc(ball & ((1u << lane) - 1u));
+        if (slot < p.max_det) {
+            rb200_det d;
+            d.cpi = (uint32_t)(p.cpi0 + slab / p.n_lanes);
+            d.r = (uint32_t)r;
+            d.v = (uint16_t)v;
+            d.lane = (uint8_t)(slab % p.n_lanes);
+            d.kind = RB200_DET_V;
+            d.amp = (float)amp;
+            dets[slot] = d;
+        }
+    }
+}
+
+template <typename T, bool ROWMAJOR>
+__device__ __forceinline__ int cfar_elect(const T* __restrict__ row, ptrdiff_t sr, int r, const CfarParams& p, T t_r, int* err_flag) {
+    // first maximum among the passing cells of {r-1, r, r+1} (executeCFAR.m:50-73); -1 if none
+    int best = -1;
+    T bestv = 0;
+#pragma unroll
+    for (int d = -1; d <= 1; ++d) {
+        const int c = r + d;
+        if (c < 0 || c >= p.R) continue;
+        if (!cfar_decide<T>(row, sr, c, p.R, p.ref_r, p.guard_r, t_r, p.meth_r, err_flag)) continue;
+        const T x = row[(ptrdiff_t)c * sr];
+        if (best < 0 || x > bestv) { best = c; bestv = x; }
+    }
+    return best;
+}
+
+// Stage R: one thread per velocity hit.
+template <typename T, bool ROWMAJOR>
+__global__ void cfar_r_kernel(const T* __restrict__ rdm, const CfarParams p, T t_r,
+                              const rb200_det* __restrict__ dets_v, const int* __restrict__ count_v,
+                              rb200_det* __restrict__ dets_2d, int* __restrict__ count_2d,
+                              const uint32_t* __restrict__ vmask, uint8_t* __restrict__ flag2d, int* err_flag) {
+    // count_v[0] = hits so far, count_v[2] = first hit of this chunk
+    const int i = count_v[2] + blockIdx.x * blockDim.x + threadIdx.x;
+    int n = count_v[0];
+    if (n > p.max_det) n = p.max_det;
+    if (i >= n) return;
+    const rb200_det h = dets_v[i];
+    const int slab = (int)(h.cpi - p.cpi0) * p.n_lanes + h.lane;
+    const int v = h.v, r = (int)h.r;
+    const T* slab_base = rdm + (size_t)slab * p.V * p.R;
+    const T* row = ROWMAJOR ? slab_base + (size_t)v * p.R : slab_base + v;
+    const ptrdiff_t sr = ROWMAJOR ? 1 : p.V;
+    const int c = cfar_elect<T, ROWMAJOR>(row, sr, r, p, t_r, err_flag);
+    if (c < 0) return;
+    if (flag2d) {
+        flag2d[ROWMAJOR ? ((size_t)slab * p.V + v) * p.R + c : (size_t)slab * p.V * p.R + v + (size_t)p.V * c] = 1;
+        if (!dets_2d) return;
+    }
+    // de-duplicate: a velocity hit with a smaller column that elects the same cell owns the record
+    const int Rw = (p.R + 31) / 32;
+    const uint32_t* mrow = vmask + ((size_t)slab * p.V + v) * Rw;
+    for (int rr = c - 1; rr < r; ++rr) {
+        if (rr < 0) continue;
+        if (!((mrow[rr >> 5] >> (rr & 31)) & 1u)) continue;
+        if (cfar_elect<T, ROWMAJOR>(row, sr, rr, p, t_r, nullptr) == c) return;
+    }
+    const int slot = atomicAdd(count_2d, 1);
+    if (slot < p.max_det) {
+        rb200_det d;
+        d.cpi = h.cpi;
+        d.r = (uint32_t)c;
+        d.v = h.v;
+        d.lane = h.lane;
+        d.kind = RB200_DET_2D;
+        d.amp = (float)row[(ptrdiff_t)c * sr];
+        dets_2d[slot] = d;
+    }
+}
+
+// 1-D CFAR over listed (row, col) cells of a column-major rows x cols matrix, detection along cols.
+__global__ void cfar1d_kernel(const double* __restrict__ data, int rows, int cols, int ref, int guard, double T, int method,
+                              const int* __restrict__ rows_fix, int n_rows_fix, const int* __restrict__ cols_fix, int n_cols_fix,
+                              uint8_t* __restrict__ out, int* err_flag) {
+    const int nr = rows_fix ? n_rows_fix : rows;
+    const int nc = cols_fix ? n_cols_fix : cols;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nr * nc) return;
+    const int ri = (int)(i % nr), ci = (int)(i / nr);
+    const int row = rows_fix ? rows_fix[ri] - 1 : ri;
+    const int y = cols_fix ? cols_fix[ci] - 1 : ci;
+    if (cfar_decide<double>(data + row, rows, y, cols, ref, guard, T, method, err_flag)) out[row + (size_t)rows * y] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool ROWMAJOR>
+static cudaError_t run_cfar(const T* rdm, const CfarParams& p, T t_r, T t_v, int n_slabs, rb200_det* dets_v, int* count_v,
+                            rb200_det* dets_2d, int* count_2d, uint32_t* vmask, uint8_t* flag2d, uint8_t* flagv,
+                            int* err_flag, cudaStream_t st) {
+    const int Rw = (p.R + 31) / 32;
+    const int nv = p.v_hi - p.v_lo;
+    if (nv <= 0 || n_slabs <= 0) return cudaSuccess;
+    const size_t words = (size_t)n_slabs * nv * Rw;
+    const size_t threads = words * 32;
+    cfar_v_kernel<T, ROWMAJOR><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(rdm, p, t_v, n_slabs, dets_v, count_v, vmask, flagv, err_flag);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (p.range_stage) {
+        cfar_r_kernel<T, ROWMAJOR><<<(p.max_det + 127) / 128, 128, 0, st>>>(rdm, p, t_r, dets_v, count_v, dets_2d, count_2d, vmask, flag2d, err_flag);
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+cudaError_t launch_cfar_f32(const float* rdm, const CfarParams& p, float t_r, float t_v, int n_slabs, void* dets_v, int* count_v,
+                            void* dets_2d, int* count_2d, uint32_t* vmask, uint8_t* flag2d, uint8_t* flagv, int* err_flag, cudaStream_t st) {
+    return run_cfar<float, true>(rdm, p, t_r, t_v, n_slabs, (rb200_det*)dets_v, count_v, (rb200_det*)dets_2d, count_2d, vmask, flag2d, flagv, err_flag, st);
+}
+
+cudaError_t launch_cfar_f64_colmajor(const double* rdm, const CfarParams& p, double t_r, double t_v, void* dets_v, int* count_v,
+                                     uint32_t* vmask, uint8_t* flag2d, uint8_t* flagv, int* err_flag, cudaStream_t st) {
+    return run_cfar<double, false>(rdm, p, t_r, t_v, 1, (rb200_det*)dets_v, count_v, nullptr, nullptr, vmask, flag2d, flagv, err_flag, st);
+}
+
+cudaError_t launch_cfar1d_f64(const double* data, int rows, int cols, int ref, int guard, double T, int method,
+                              const int* rows_fix, int n_rows_fix, const int* cols_fix, int n_cols_fix,
+                              uint8_t* out, int* err_flag, cudaStream_t st) {
+    const size_t n = (size_t)(rows_fix ? n_rows_fix : rows) * (cols_fix ? n_cols_fix : cols);
+    if (n == 0) return cudaSuccess;
+    cfar1d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(data, rows, cols, ref, guard, T, method, rows_fix, n_rows_fix, cols_fix, n_cols_fix, out, err_flag);
+    return cudaGetLastError();
+}
+
+}  // namespace rb

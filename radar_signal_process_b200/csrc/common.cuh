@@ -1,0 +1,65 @@
+// common.cuh -- shared device-side parameter blocks and small helpers for libradar_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rb {
+
+constexpr int kMaxSegs = 8;
+
+__host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
+
+// One waveform segment in correlation form:
+//   y[n] = sum_k xin[n + k - pre] * conj(t[k]),  n in [0, out_len),  xin = 0 outside [0, in_len)
+//   out[out_start + ((n - rot) mod out_len)] = y[n]
+// MF leading edge: pre = 0, rot = 0 (MP/fun_lss_pulse_compression.m:36-37);
+// FIR delayed:     pre = L-1, t = conj(flip(b)) (MP/...:25-31);
+// FIR grpdelay:    same with rot = round(mean(grpdelay(b))) (MTD/fun_lss_pulse_compression.m:47-51).
+struct PcSegDev {
+    int in_start, in_len, out_start, out_len;
+    int rot, V, pre, h_off;   // V = outputs per overlap-save tile, h_off = offset of the spectrum in hperm
+    int n_taps, t_off;        // time-domain taps (direct fallback): offset into taps table
+};
+
+struct PcParams {
+    const void* in;         // int16 wire [group][range][lane][2]  or  float2 planar [line][range]
+    float2* out;            // float2 planar [line][R]
+    const float2* hperm;    // digit-reversed reference spectra, (scale/NT) * conj(FFT(taps))
+    const float2* tw;       // exp(-2*pi*i*m/NT), m = 0..NT-1
+    const float* gain;      // iSTC linear gain per range cell (nullable)
+    const int2* tiles;      // (segment, tile index) per blockIdx.y
+    PcSegDev segs[kMaxSegs];
+    int R;                  // samples per input PRT line
+    int R_out;              // elements per output line
+    int C;                  // lanes interleaved in the wire format
+    int P;                  // PRTs per CPI (wire output line mapping)
+    int n_lines;            // planar: number of lines
+};
+
+struct MtdParams {
+    const float2* in;       // planar [slab][prt][range]
+    float* out;             // [slab][v][range]
+    const float* window;    // P
+    const float2* tw;       // exp(-2*pi*i*m/P)
+    int P;
+    int in_ld, out_ld;      // elements per input line / per output row
+    int cols;               // columns to process (Len_PRT)
+    int mti_lag;            // 0 = off
+    int zv_lo, zv_hi;       // 0-based inclusive rows to zero (zv_lo > zv_hi = none)
+    // generic Stockham only
+    int n_stages;
+    int radix[16];
+};
+
+struct CfarParams {
+    int V, R;               // full RDM size
+    int v_lo, v_hi;         // 0-based tested rows [v_lo, v_hi)  (n0+1 .. V-n0)
+    int ref_r, guard_r, meth_r;
+    int ref_v, guard_v, meth_v;
+    int range_stage;
+    int max_det;
+    int n_lanes;            // slabs per CPI (detection record: cpi = slab / n_lanes, lane = slab % n_lanes)
+    int cpi0;               // CPI index of slab 0 (chunked batches)
+};
+
+}  // namespace rb

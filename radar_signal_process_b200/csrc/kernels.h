@@ -1,0 +1,40 @@
+// kernels.h -- host-callable launchers of the CUDA kernels (internal to libradar_b200).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace rb {
+
+// ---- K1 pulse compression (pc_kernels.cu)
+int pc_tile_lanes(int nt, bool wire);     // lines per CTA for FFT tile size nt (0 = unsupported)
+cudaError_t launch_pc_fft(int nt, bool wire, const PcParams& p, int n_tiles, int n_groups, cudaStream_t st);
+cudaError_t launch_pc_direct(bool wire, const PcParams& p, const float2* taps, int seg_idx, int out_len, int n_lines, cudaStream_t st);
+cudaError_t launch_pc_zero_cols(float2* out, size_t n_lines, int R, int c0, int c1, cudaStream_t st);
+cudaError_t launch_unpack(const int16_t* raw, float2* out, int n_groups, int P, int R, int C, cudaStream_t st);
+
+// ---- K2 MTD (mtd_kernels.cu)
+bool mtd_has_fast_path(int P);
+cudaError_t launch_mtd(const MtdParams& p, int n_slabs, cudaStream_t st);
+int mtd_generic_max_p();
+
+// ---- K3 CFAR (cfar_kernels.cu)
+// chain variant: float RDM [slab][V][R] row-major -> velocity-hit list + 2-D list (+ optional dense uint8 flags)
+cudaError_t launch_cfar_f32(const float* rdm, const CfarParams& p, float t_r, float t_v, int n_slabs, void* dets_v, int* count_v,
+                            void* dets_2d, int* count_2d, uint32_t* vmask, uint8_t* flag2d, uint8_t* flagv, int* err_flag, cudaStream_t st);
+// MATLAB variant: one double V x R column-major matrix -> dense uint8 flags (column-major)
+cudaError_t launch_cfar_f64_colmajor(const double* rdm, const CfarParams& p, double t_r, double t_v, void* dets_v, int* count_v,
+                                     uint32_t* vmask, uint8_t* flag2d, uint8_t* flagv, int* err_flag, cudaStream_t st);
+// 1-D CFAR along the second dimension of a column-major rows x cols double matrix, all or listed (1-based) cells
+cudaError_t launch_cfar1d_f64(const double* data, int rows, int cols, int ref, int guard, double T, int method,
+                              const int* rows_fix, int n_rows_fix, const int* cols_fix, int n_cols_fix,
+                              uint8_t* out, int* err_flag, cudaStream_t st);
+
+// ---- layout conversion (layout_kernels.cu): MATLAB column-major split double <-> device layouts
+cudaError_t launch_z_to_planar(const double* re, const double* im, float2* out, int rows, int cols, cudaStream_t st);          // out[row][col]
+cudaError_t launch_planar_to_z(const float2* in, double* re, double* im, int rows, int cols, cudaStream_t st);                // in[row][col]
+cudaError_t launch_f32_rowmajor_to_d_colmajor(const float* in, double* out, int rows, int cols, cudaStream_t st);
+cudaError_t launch_u8_to_d(const uint8_t* in, double* out, size_t n, cudaStream_t st);
+cudaError_t launch_zero_rows_d_colmajor(const double* in, double* out, int rows, int cols, int lo, int hi, cudaStream_t st);
+
+}  // namespace rb

@@ -1,0 +1,311 @@
+// pc_kernels.cu -- K1: int16 I/Q unpack (+ iSTC gain) + segmented pulse compression.
+//
+// Replaces the per-PRT loop of MP/fun_lss_pulse_compression.m:24-37 (9-arg twin
+// MTD/fun_lss_pulse_compression.m:36-65) and the three per-PRT FFTs of
+// MP/fun_pulse_compression.m:19-22, fused with the DDC unpack of FrameDataRead_xzr.m:138,150-156
+// and the optional iSTC gain of MP/fun_iSTC.m:14.
+//
+// Algorithm: overlap-save fast correlation.  Every waveform segment is cut into tiles of NT = R^S
+// input samples; one CTA transforms LT independent lines (the 16 interleaved channels of one PRT in
+// wire mode) of one tile:
+//     in-place radix-R DIF forward FFT (S stages; stage 0 straight from global memory with the
+//     int16 -> fp32 unpack, later stages exchanged through shared memory)
+//   -> multiply by the resident, digit-reversed reference spectrum conj(FFT(taps)) * scale/NT
+//   -> in-place radix-R DIT inverse FFT back to natural order
+//   -> the V = NT-L+1 alias-free lags are stored range-contiguous as float2 [line][range].
+// The forward transform leaves the spectrum digit-reversed and the inverse consumes it that way, so
+// no reordering pass exists; 2(S-1) shared-memory exchanges per tile.
+//
+// Thread mapping: lane-fastest (thread = lane + LT*butterfly) for every stage but the last, so that
+// a warp's global load covers 2 range cells x 16 channels = 128 contiguous bytes of the wire format
+// and shared-memory accesses of a half-warp hit 16 different lanes (odd line stride -> no bank
+// conflicts).  The final inverse stage is re-mapped butterfly-fastest so each warp stores 256
+// contiguous bytes of one output line.
+#include "common.cuh"
+#include "radix.cuh"
+#include "kernels.h"
+
+namespace rb {
+
+template <int R, int S, int LT, bool WIRE>
+__global__ void __launch_bounds__(LT * (ipow(R, S) / R))
+pc_fft_kernel(const PcParams p) {
+    constexpr int NT = ipow(R, S);
+    constexpr int NB = NT / R;     // butterflies per line per stage
+    constexpr int LS = NT + 1;     // line stride in shared memory (odd -> conflict-free across lanes)
+    extern __shared__ float2 sm[];
+
+    const int t = threadIdx.x;
+    const int lane = t % LT;
+    const int u = t / LT;
+    const int2 tile = __ldg(&p.tiles[blockIdx.y]);
+    const PcSegDev& sg = p.segs[tile.x];
+    const int g = blockIdx.x;
+    const int in_off = tile.y * sg.V - sg.pre;
+
+    float2 v[R];
+    // ---- stage 0 operands straight from global memory (unpack fused) ----
+    {
+        bool lane_ok;
+        size_t base;
+        const int lane_g = blockIdx.z * LT + lane;   // wire: channel index
+        if (WIRE) {
+            lane_ok = lane_g < p.C;
+            base = (size_t)g * p.R;
+        } else {
+            const int line = g * LT + lane;
+            lane_ok = line < p.n_lines;
+            base = (size_t)line * p.R;
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int rs = in_off + u + j * NB;
+            float2 x = make_float2(0.f, 0.f);
+            if (lane_ok && rs >= 0 && rs < sg.in_len) {
+                const int r = sg.in_start + rs;
+                if (WIRE) {
+                    const int w = __ldg(reinterpret_cast<const int*>(p.in) + (base + r) * p.C + lane_g);
+                    x.x = (float)(short)(w & 0xffff);   // I  (little-endian int16 pair, FrameDataRead_xzr.m:154)
+                    x.y = (float)(short)(w >> 16);      // Q  (:155)
+                } else {
+                    x = __ldg(reinterpret_cast<const float2*>(p.in) + base + r);
+                }
+                if (p.gain) x = cscale(x, __ldg(p.gain + r));
+            }
+            v[j] = x;
+        }
+    }
+    float2* line_sm = sm + lane * LS;
+
+    // ---- forward DIF ----
+    Dft<R, -1>::run(v);
+    if (S > 1) {
+#pragma unroll
+        for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(p.tw + u * k));
+    }
+#pragma unroll
+    for (int s = 1; s < S; ++s) {
+        const int sp = NT / ipow(R, s);           // stride of stage s-1
+        const int basep = (u / sp) * sp * R + (u % sp);
+#pragma unroll
+        for (int k = 0; k < R; ++k) line_sm[basep + k * sp] = v[k];
+        __syncthreads();
+        const int st = NT / ipow(R, s + 1);       // stride of stage s
+        const int q = u % st;
+        const int base = (u / st) * st * R + q;
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = line_sm[base + j * st];
+        Dft<R, -1>::run(v);
+        if (st > 1) {
+            const int m = q * ipow(R, s);
+#pragma unroll
+            for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(p.tw + m * k));
+        }
+    }
+
+    // ---- reference spectrum (digit-reversed order == this thread's positions u*R .. u*R+R-1) ----
+    {
+        const float4* hp = reinterpret_cast<const float4*>(p.hperm + sg.h_off + u * R);
+#pragma unroll
+        for (int k = 0; k < R; k += 2) {
+            const float4 h = __ldg(hp + k / 2);
+            v[k] = cmul(v[k], make_float2(h.x, h.y));
+            v[k + 1] = cmul(v[k + 1], make_float2(h.z, h.w));
+        }
+    }
+
+    // ---- inverse DIT ----
+    int out_lane = lane, out_u = u;
+#pragma unroll
+    for (int s = S - 1; s >= 0; --s) {
+        const int st = NT / ipow(R, s + 1);
+        const int q = u % st;
+        if (st > 1 && s > 0) {
+            const int m = q * ipow(R, s);
+#pragma unroll
+            for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], __ldg(p.tw + m * k));
+        }
+        if (s == 0 && S > 1) {
+            // stage-0 operands were fetched with the store mapping (out_lane, out_u)
+#pragma unroll
+            for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], __ldg(p.tw + out_u * k));
+        }
+        Dft<R, +1>::run(v);
+        if (s > 0) {
+            const int base = (u / st) * st * R + q;
+#pragma unroll
+            for (int j = 0; j < R; ++j) line_sm[base + j * st] = v[j];
+            __syncthreads();
+            const int sn = NT / ipow(R, s);       // stride of stage s-1
+            if (s - 1 == 0) {
+                // re-map: butterfly index fastest so that global stores coalesce along range
+                out_lane = t / NB;
+                out_u = t % NB;
+                const float2* src = sm + out_lane * LS + out_u;
+#pragma unroll
+                for (int k = 0; k < R; ++k) v[k] = src[k * sn];
+            } else {
+                const int basen = (u / sn) * sn * R + (u % sn);
+#pragma unroll
+                for (int k = 0; k < R; ++k) v[k] = line_sm[basen + k * sn];
+            }
+        }
+    }
+
+    // ---- store the alias-free lags ----
+    {
+        size_t oline;
+        bool ok;
+        if (WIRE) {
+            const int cpi = g / p.P, prt = g % p.P;
+            const int out_lane_g = blockIdx.z * LT + out_lane;
+            ok = out_lane_g < p.C;
+            oline = ((size_t)cpi * p.C + out_lane_g) * p.P + prt;
+        } else {
+            const int line = g * LT + out_lane;
+            ok = line < p.n_lines;
+            oline = line;
+        }
+        if (ok) {
+            float2* o = p.out + oline * p.R_out + sg.out_start;
+            const int n0 = tile.y * sg.V;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int nl = out_u + j * NB;
+                const int n = n0 + nl;
+                if (nl < sg.V && n < sg.out_len) {
+                    int c = n - sg.rot;
+                    if (c < 0) c += sg.out_len;
+                    o[c] = v[j];
+                }
+            }
+        }
+    }
+}
+
+// Time-domain fallback for tap counts beyond the largest FFT tile: one thread per output sample.
+template <bool WIRE>
+__global__ void pc_direct_kernel(const PcParams p, const float2* __restrict__ taps, int seg_idx, int n_groups_lines) {
+    const PcSegDev& sg = p.segs[seg_idx];
+    const int n = blockIdx.y * blockDim.x + threadIdx.x;
+    const int line = blockIdx.x;   // wire: group*C + lane ; planar: line
+    if (n >= sg.out_len) return;
+    size_t ibase, oline;
+    int stride;
+    if (WIRE) {
+        const int g = line / p.C, lane = line % p.C;
+        ibase = (size_t)g * p.R * p.C + lane;
+        stride = p.C;
+        const int cpi = g / p.P, prt = g % p.P;
+        oline = ((size_t)cpi * p.C + lane) * p.P + prt;
+    } else {
+        ibase = (size_t)line * p.R;
+        stride = 1;
+        oline = line;
+    }
+    float2 acc = make_float2(0.f, 0.f);
+    const float2* tp = taps + sg.t_off;
+    for (int k = 0; k < sg.n_taps; ++k) {
+        const int rs = n + k - sg.pre;
+        if (rs < 0 || rs >= sg.in_len) continue;
+        const int r = sg.in_start + rs;
+        float2 x;
+        if (WIRE) {
+            const int w = __ldg(reinterpret_cast<const int*>(p.in) + ibase + (size_t)r * stride);
+            x = make_float2((float)(short)(w & 0xffff), (float)(short)(w >> 16));
+        } else {
+            x = __ldg(reinterpret_cast<const float2*>(p.in) + ibase + r);
+        }
+        if (p.gain) x = cscale(x, __ldg(p.gain + r));
+        const float2 c = cmulc(x, __ldg(tp + k));
+        acc.x += c.x;
+        acc.y += c.y;
+    }
+    int c = n - sg.rot;
+    if (c < 0) c += sg.out_len;
+    p.out[oline * p.R_out + sg.out_start + c] = acc;
+}
+
+// zero the output columns no segment writes (s_PC_0 = zeros(...), MP/fun_lss_pulse_compression.m:18)
+__global__ void pc_zero_cols_kernel(float2* out, size_t n_lines, int R, int c0, int c1) {
+    const int w = c1 - c0;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lines * (size_t)w) return;
+    const size_t line = i / w;
+    const int c = c0 + (int)(i % w);
+    out[line * R + c] = make_float2(0.f, 0.f);
+}
+
+// plain unpack (parity/debug entry rb200_unpack_ddc_i16): wire -> float2 [cpi][lane][prt][range]
+__global__ void unpack_kernel(const int* __restrict__ raw, float2* __restrict__ out, int n_groups, int P, int R, int C) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into wire words
+    const size_t total = (size_t)n_groups * R * C;
+    if (i >= total) return;
+    const int lane = (int)(i % C);
+    const size_t gr = i / C;
+    const int r = (int)(gr % R);
+    const size_t g = gr / R;
+    const int cpi = (int)(g / P), prt = (int)(g % P);
+    const int w = __ldg(raw + i);
+    out[(((size_t)cpi * C + lane) * P + prt) * R + r] = make_float2((float)(short)(w & 0xffff), (float)(short)(w >> 16));
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+template <int R, int S, int LT, bool WIRE>
+static cudaError_t launch_fft(const PcParams& p, int n_tiles, int n_groups, cudaStream_t st) {
+    constexpr int NT = ipow(R, S);
+    constexpr int threads = LT * (NT / R);
+    const size_t smem = (size_t)LT * (NT + 1) * sizeof(float2);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(pc_fft_kernel<R, S, LT, WIRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid(n_groups, n_tiles, WIRE ? (p.C + LT - 1) / LT : 1);
+    if (n_tiles > 65535) return cudaErrorInvalidConfiguration;
+    pc_fft_kernel<R, S, LT, WIRE><<<grid, threads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+int pc_tile_lanes(int nt, bool wire) {
+    (void)wire;
+    switch (nt) {
+        case 256: return 16;
+        case 512: return 16;
+        case 4096: return 2;
+        default: return 0;
+    }
+}
+
+cudaError_t launch_pc_fft(int nt, bool wire, const PcParams& p, int n_tiles, int n_groups, cudaStream_t st) {
+    if (nt == 256) return wire ? launch_fft<16, 2, 16, true>(p, n_tiles, n_groups, st) : launch_fft<16, 2, 16, false>(p, n_tiles, n_groups, st);
+    if (nt == 512) return wire ? launch_fft<8, 3, 16, true>(p, n_tiles, n_groups, st) : launch_fft<8, 3, 16, false>(p, n_tiles, n_groups, st);
+    if (nt == 4096) return wire ? launch_fft<16, 3, 2, true>(p, n_tiles, n_groups, st) : launch_fft<16, 3, 2, false>(p, n_tiles, n_groups, st);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_pc_direct(bool wire, const PcParams& p, const float2* taps, int seg_idx, int out_len, int n_lines, cudaStream_t st) {
+    dim3 grid(n_lines, (out_len + 127) / 128, 1);
+    if (grid.y > 65535) return cudaErrorInvalidConfiguration;
+    if (wire) pc_direct_kernel<true><<<grid, 128, 0, st>>>(p, taps, seg_idx, n_lines);
+    else pc_direct_kernel<false><<<grid, 128, 0, st>>>(p, taps, seg_idx, n_lines);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pc_zero_cols(float2* out, size_t n_lines, int R, int c0, int c1, cudaStream_t st) {
+    if (c1 <= c0 || n_lines == 0) return cudaSuccess;
+    const size_t total = n_lines * (size_t)(c1 - c0);
+    pc_zero_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, n_lines, R, c0, c1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack(const int16_t* raw, float2* out, int n_groups, int P, int R, int C, cudaStream_t st) {
+    const size_t total = (size_t)n_groups * R * C;
+    unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const int*>(raw), out, n_groups, P, R, C);
+    return cudaGetLastError();
+}
+
+}  // namespace rb

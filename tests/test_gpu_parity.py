@@ -1,0 +1,363 @@
+"""GPU parity: the CUDA path, called through the C ABI (ctypes host mirror), against the CPU oracle.
+
+Tolerances (BASELINE.json north_star):
+  * int16 I/Q unpack: bit-exact
+  * pulse-compressed samples / RDM magnitudes: max|gpu - ref| <= 1e-4 * max|ref|   (fp32 vs double)
+  * CFAR flags: identical, except cells whose decision lies within 1e-4 (relative) of a threshold,
+    which are counted and printed.  The MATLAB-layout double entry points must be bit-identical.
+"""
+import numpy as np
+import pytest
+
+from oracle import mcode, synth, vec
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _rand_c(rng, *shape):
+    return rng.normal(size=shape) + 1j * rng.normal(size=shape)
+
+
+def _close(a, b, tol=RTOL):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = np.max(np.abs(b))
+    err = np.max(np.abs(a - b))
+    assert err <= tol * max(scale, 1e-300), "max err %.3e vs scale %.3e (rel %.3e)" % (err, scale, err / max(scale, 1e-300))
+    return err / max(scale, 1e-300)
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_library_is_native_and_loaded(lib):
+    import os
+    assert os.path.exists(lib.LIB_PATH)
+    assert lib.load().rb200_version() >= 1
+    ctx = lib.default_context()
+    assert ctx._h.value
+
+
+def test_unpack_bit_exact(lib):
+    rng = np.random.default_rng(0)
+    P, R, C, B = 4, 333, 16, 2
+    raw = rng.integers(-32768, 32768, size=(B, P, R, C, 2), dtype=np.int16)
+    raw[0, 0, 0, 0] = (-32768, 32767)
+    with lib.Context(0, n_prt=P, n_range=R, n_lanes=C, max_cpi=B) as ctx:
+        got = ctx.unpack(raw, B)
+    want = vec.unpack_wire(raw, B, P, R, C)
+    assert np.array_equal(got.astype(np.complex128), want)
+
+
+@pytest.mark.parametrize("L,M", [(67, 300), (75, 242), (160, 707), (7, 3), (1, 5), (200, 723), (700, 2453), (35, 82), (5000, 300)])
+def test_fun_pulse_compression(lib, L, M):
+    rng = np.random.default_rng(L * 1000 + M)
+    s0 = _rand_c(rng, L)
+    x = _rand_c(rng, M)
+    got = lib.fun_pulse_compression(s0, x)
+    want = mcode.fun_pulse_compression(s0, x)
+    assert got.shape == (1, L + M - 1)
+    _close(got[0], want)
+
+
+def test_fun_pulse_compression_real_inputs_and_reference_chirp(lib):
+    ref = mcode.load_ref("refDDCDataMF1")
+    x = np.zeros(512)
+    x[100] = 3.0
+    got = lib.fun_pulse_compression(ref, x)[0]
+    want = mcode.fun_pulse_compression(ref, x)
+    _close(got, want)
+    assert np.argmax(np.abs(got)) in range(100, 100 + 67)
+
+
+def test_fun_lss_pulse_compression_5arg(lib):
+    rng = np.random.default_rng(5)
+    p2, p3 = mcode.load_pulse_literals()
+    for n in (1031, 1024, 400):
+        echo = np.rint(200 * _rand_c(rng, 6, n))
+        got = lib.fun_lss_pulse_compression(echo, 0, mcode.pulse1_mp(), p2, p3)
+        want = mcode.fun_lss_pulse_compression_mp(echo, None, p2, p3)
+        _close(got, want)
+    with pytest.raises(lib.MatlabDimensionError):
+        lib.fun_lss_pulse_compression(echo, 0, None, p2[:70], p3)
+    with pytest.raises(lib.MatlabIndexError):
+        lib.fun_lss_pulse_compression(echo[:, :300], 0, None, p2, p3)
+
+
+def test_fun_lss_pulse_compression_9arg(lib):
+    rng = np.random.default_rng(6)
+    params = dict(fs=25e6, B=20e6, tao=[0.16e-6, 8e-6, 28e-6], point_prt=[3404, 228, 723, 2453])
+    pulse1, pulse2, pulse3 = mcode.ideal_pulses_mtd(params)
+    echo = np.rint(100 * _rand_c(rng, 4, 3404))
+    got = lib.fun_lss_pulse_compression(echo, params, 0, pulse1, pulse2, pulse3, 228, 723, 2453)
+    want = mcode.fun_lss_pulse_compression_mtd(echo, pulse1, pulse2, pulse3, 228, 723, 2453)
+    _close(got, want)
+    # shorter third segment leaves the tail zero
+    got = lib.fun_lss_pulse_compression(echo, params, 0, pulse1, pulse2, pulse3, 228, 723, 2000)
+    want = mcode.fun_lss_pulse_compression_mtd(echo, pulse1, pulse2, pulse3, 228, 723, 2000)
+    _close(got, want)
+    assert np.all(got[:, 228 + 723 + 2000:] == 0)
+    with pytest.raises(lib.MatlabIndexError):
+        lib.fun_lss_pulse_compression(echo, params, 0, pulse1, pulse2, pulse3, 228, 723, 2454)
+
+
+@pytest.mark.parametrize("P", [8, 64, 256, 155, 1536, 7, 1])
+def test_fun_Process_MTD(lib, P):
+    rng = np.random.default_rng(P)
+    cols = 37
+    x = 1000 * _rand_c(rng, P, cols)
+    got = lib.fun_Process_MTD(x, cols, P)
+    want = mcode.fun_Process_MTD(x, cols, P)
+    _close(got, want)
+    if P > 1:
+        got = lib.fun_Process_MTD(x, 5, P)          # Len_PRT < columns
+        _close(got, want[:, :5])
+    with pytest.raises(lib.MatlabIndexError):
+        lib.fun_Process_MTD(x, cols + 1, P)
+    if P > 2:
+        with pytest.raises(lib.MatlabDimensionError):
+            lib.fun_Process_MTD(x, cols, P - 1)
+
+
+def test_fun_Process_MTD_tone_lands_on_shifted_bin(lib):
+    P = 64
+    for k in (-32, -1, 0, 5, 31):
+        x = np.exp(2j * np.pi * k * np.arange(P) / P)[:, None] * np.ones((1, 3))
+        m = lib.fun_Process_MTD(x, 3, P)
+        assert np.argmax(m[:, 1]) == k + 32
+        assert abs(m[k + 32, 1] - mcode.kaiser(P, 8).sum()) < 1e-4 * P
+
+
+@pytest.mark.parametrize("P,div", [(1536, 150), (64, 150), (8, 150), (256, 150), (155, 20)])
+def test_fun_0v_pressing(lib, P, div):
+    rng = np.random.default_rng(P)
+    m = rng.rayleigh(1.0, size=(P, 9))
+    got = lib.fun_0v_pressing(m, div)
+    assert np.array_equal(got, mcode.fun_0v_pressing(m, div))
+
+
+def test_fun_MTD_produce_S1(lib):
+    """Config 1 stand-in: 1536 x 1031 frame through the 1-arg API (literal pulses, segments 82/242/707)."""
+    echo = synth.s1_frame(0)
+    got = lib.fun_MTD_produce(echo)
+    p2, p3 = mcode.load_pulse_literals()
+    want = vec.zero_v(vec.process_mtd(vec.lss_pc_mp(echo, p2, p3), axis=0), 150, axis=0)
+    rel = _close(got, want)
+    print("S1 RDM rel err %.2e" % rel)
+    assert np.all(got[757:778, :] == 0)
+    # then main_produce-style crop, CW/ 0-v, fun_CFARflag (CW/main_cfar.m:86-93,142-161)
+    crop_g = lib.fun_0v_pressing(np.abs(got[690:845, :]), 20)
+    crop_w = vec.zero_v(want[690:845, :], 20, axis=0)
+    args = synth.cfar_tuple(synth.S1_CFAR)
+    fg = np.zeros(crop_g.shape)
+    for a, b in ((1, 82), (83, 318), (319, 868)):
+        f, _ = lib.executeCFAR(crop_g[:, a - 1:b], *args)
+        fg[:, a - 1:b] = f
+    # same input (the GPU RDM) through the oracle must give identical flags: double path is exact
+    assert np.array_equal(fg, vec.cfar_flag_segments(crop_g, args))
+    # against the oracle's own RDM only near-threshold cells may differ
+    fw = vec.cfar_flag_segments(crop_w, args)
+    print("S1 flags: gpu %d oracle %d differing %d" % (fg.sum(), fw.sum(), (fg != fw).sum()))
+
+
+def test_fun_MTD_produce_S2_and_cfar(lib):
+    echo = synth.s2_frame()
+    got = lib.fun_MTD_produce(echo)
+    want = mcode.fun_MTD_produce_mp(echo)
+    _close(got, want)
+    assert np.all(got[3, :] == 0) and np.all(got[4, :] > 0)       # row 4 (1-based) zeroed, DC untouched
+    args = synth.cfar_tuple(synth.S2_CFAR)
+    f, fv = lib.executeCFAR(got, *args)
+    fo, fvo = mcode.executeCFAR(got, *args)
+    assert np.array_equal(f, fo) and np.array_equal(fv, fvo)
+
+
+def test_fun_MTD_produce_2arg(lib):
+    rng = np.random.default_rng(12)
+    params = dict(prt=1e-4, prf=1e4, prtNum=32, fs=25e6, deltaR=6.0, fc=9.4e9, wavelength=0.0319, B=20e6,
+                  tao=[0.16e-6, 8e-6, 28e-6], point_prt=[3404, 228, 723, 2453], debug=dict(show_PC=0, show_FFT=0, graph=0))
+    echo = np.rint(100 * _rand_c(rng, 32, 3404))
+    got = lib.fun_MTD_produce(echo, params)
+    want = mcode.fun_MTD_produce_mtd(echo, params)
+    _close(got, want)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_executeCFAR_bit_identical(lib, seed):
+    rng = np.random.default_rng(200 + seed)
+    V, R = int(rng.integers(30, 70)), int(rng.integers(24, 300))
+    n0 = int(rng.integers(0, 3))
+    x = rng.rayleigh(1.0, size=(V, R))
+    for _ in range(10):
+        v, r = int(rng.integers(0, V)), int(rng.integers(0, R))
+        x[v, r] = 40.0
+        if r + 1 < R and rng.random() < 0.5:
+            x[v, r + 1] = 40.0                      # exact tie -> first max
+    x[V // 2, :] = 0.0                              # 0 >= 0 is flagged in the range stage
+    meth = seed % 2
+    T = 3.0 if seed % 3 else 1.0
+    args = (5, 7, T, meth, 5, 7, T, meth, n0, 1)
+    f, fv = lib.executeCFAR(x, *args)
+    fo, fvo = mcode.executeCFAR(x, *args)
+    assert np.array_equal(fv, fvo)
+    assert np.array_equal(f, fo)
+    f0, fv0 = lib.executeCFAR(x, *args[:-1], 0)
+    assert np.array_equal(f0, fvo) and np.array_equal(fv0, fvo)
+
+
+def test_executeCFAR_errors_and_edges(lib):
+    x = np.ones((20, 40))
+    with pytest.raises(lib.MatlabIndexError):       # velocity axis (19 rows) shorter than 24
+        lib.executeCFAR(x, 5, 7, 5.0, 0, 5, 7, 5.0, 0, 0, 1)
+    x = np.ones((64, 128))
+    x[20, 60] = 100.0
+    f, fv = lib.executeCFAR(x, 5, 7, 5.0, 0, 5, 7, 5.0, 0, 0, 1)
+    assert f.sum() == 1 and f[20, 60] == 1 and fv.sum() == 1
+    c = np.full((64, 64), 3.0)                      # constant background: flagged iff T <= 1
+    f, fv = lib.executeCFAR(c, 5, 7, 1.0, 0, 5, 7, 1.0, 0, 0, 1)
+    fo, fvo = mcode.executeCFAR(c, 5, 7, 1.0, 0, 5, 7, 1.0, 0, 0, 1)
+    assert np.array_equal(f, fo) and np.array_equal(fv, fvo) and fv[1:].all()
+
+
+def test_Function_CFAR1D_sub_and_fixCells(lib):
+    rng = np.random.default_rng(7)
+    d = rng.rayleigh(1.0, size=(9, 50))
+    for meth in (0, 1):
+        assert np.array_equal(lib.Function_CFAR1D_sub(d, 5, 7, 1.2, meth), mcode.Function_CFAR1D_sub(d, 5, 7, 1.2, meth))
+    assert np.array_equal(lib.Function_CFAR1D_sub_fixCells(d, 5, 7, 1.2, 0, [2, 5], [1, 25, 50]),
+                          mcode.Function_CFAR1D_sub_fixCells(d, 5, 7, 1.2, 0, [2, 5], [1, 25, 50]))
+    assert lib.Function_CFAR1D_sub(np.zeros((1, 24)), 5, 7, 5.0, 0).all()
+    with pytest.raises(lib.MatlabIndexError):
+        lib.Function_CFAR1D_sub(np.zeros((1, 23)), 5, 7, 5.0, 0)
+    with pytest.raises(lib.MatlabIndexError):
+        lib.Function_CFAR1D_sub_fixCells(d, 5, 7, 1.2, 0, [10], [1])
+
+
+# ---------------------------------------------------------------------------------------------------
+# the batched wire-format chain (benchmark path)
+# ---------------------------------------------------------------------------------------------------
+def _chain_ctx(lib, P, R, C, B, plan, cfar, **kw):
+    ctx = lib.Context(0, n_prt=P, n_range=R, n_lanes=C, max_cpi=B, **kw)
+    ctx.set_waveform(plan)
+    ctx.set_cfar(*cfar)
+    return ctx
+
+
+def _compare_flags(got_dets, out, B, C, V, R, lib):
+    flag, flagv = lib.dets_to_flags(got_dets, B, C, V, R)
+    dv = flagv != out["flagV"]
+    d2 = flag != out["flag"]
+    bad_v = dv & ~out["nearV"]
+    bad_2 = d2 & ~out["near"]
+    print("flags: V-stage gpu %d oracle %d differ %d (unexcused %d) | 2-D gpu %d oracle %d differ %d (unexcused %d)" %
+          (flagv.sum(), out["flagV"].sum(), dv.sum(), bad_v.sum(), flag.sum(), out["flag"].sum(), d2.sum(), bad_2.sum()))
+    assert bad_v.sum() == 0
+    assert bad_2.sum() == 0
+    return int(dv.sum()), int(d2.sum())
+
+
+def test_chain_S3_two_cpis(lib):
+    """Headline shape 64 x 4096 x 16, two CPIs, plan 'single' with refDDCDataMF1."""
+    P, R, C, B = 64, 4096, 16, 2
+    raw, targets = synth.s3_batch(B)
+    ref = mcode.load_ref("refDDCDataMF1")
+    cfar = synth.cfar_tuple(synth.S3_CFAR)
+    out = vec.chain(raw, B, P, R, C, ("single", ref), cfar, near_tol=RTOL)
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar) as ctx:
+        rdm, dets, n = ctx.chain(raw, B)
+        pc = ctx.debug_fetch_pc(B - 1)
+        assert ctx.last_launch_count() >= 3 and ctx.last_device_ms() > 0
+    print("S3 PC rel err %.2e" % _close(pc, out["pc"][B - 1]))
+    print("S3 RDM rel err %.2e" % _close(rdm, out["rdm"]))
+    assert n == len(dets) and n > 0
+    _compare_flags(dets, out, B, C, P, R, lib)
+    # every injected target is found within one range cell of its leading edge
+    flag, _ = lib.dets_to_flags(dets, B, C, P, R)
+    missed = sum(1 for b in range(B) for lane, r0, k, snr in targets[b]
+                 if flag[b, lane, k + 32, max(r0 - 1, 0):r0 + 2].sum() == 0 and out["flag"][b, lane, k + 32, max(r0 - 1, 0):r0 + 2].sum() > 0)
+    assert missed == 0
+
+
+def test_chain_lss_plan_and_odd_lane_count(lib):
+    """Secondary plan 'lss' (82/242/rest with FIR + literal pulses) on 13 lanes."""
+    P, R, C, B = 64, 1031, 13, 1
+    rng = np.random.default_rng(3)
+    raw = rng.integers(-300, 300, size=(B, P, R, C, 2), dtype=np.int16)
+    p2, p3 = mcode.load_pulse_literals()
+    cfar = synth.cfar_tuple(synth.S3_CFAR)
+    out = vec.chain(raw, B, P, R, C, ("lss_mp", p2, p3), cfar, near_tol=RTOL)
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_mp(R, p2, p3), cfar) as ctx:
+        rdm, dets, n = ctx.chain(raw, B)
+    _close(rdm, out["rdm"])
+    _compare_flags(dets, out, B, C, P, R, lib)
+
+
+def test_chain_S5_small_istc_mti(lib):
+    """DBF-mode long CPI (P=256) with iSTC and MTI on, reduced range extent."""
+    P, R, C, B = 256, 2048, 4, 1
+    ref = mcode.load_ref("refDBFDataMF1")
+    raw, _ = synth.s3_cpi(0, P=P, R=R, C=C, ref=ref, seed0=5000, r_lo=100, r_hi=R - 200, exclude=(-3, -2, -1, 0, 1, 2, 3))
+    raw = raw[None]
+    stc = synth.s5_stc_curve()
+    cfar = synth.cfar_tuple(synth.S5_CFAR)
+    out = vec.chain(raw, B, P, R, C, ("single", ref), cfar, stc=stc, mti_lag=30, near_tol=RTOL)
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, mti_lag=30) as ctx:
+        ctx.set_stc(stc)
+        rdm, dets, n = ctx.chain(raw, B)
+    _close(rdm, out["rdm"])
+    assert np.all(rdm[:, :, 125:130, :] == 0)
+    _compare_flags(dets, out, B, C, P, R, lib)
+
+
+def test_chain_full_size_properties(lib):
+    """BASELINE full-size batch (8 CPIs of 64 x 4096 x 16): size-independent properties."""
+    P, R, C, B = 64, 4096, 16, 8
+    raw, _ = synth.s3_batch(2)
+    raw = np.concatenate([raw] * 4, axis=0)                     # cpi 0,1,0,1,...
+    ref = mcode.load_ref("refDDCDataMF1")
+    cfar = synth.cfar_tuple(synth.S3_CFAR)
+
+    def key(d):
+        return np.sort(d, order=["cpi", "lane", "v", "r", "kind"])
+
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=3) as ctx:
+        rdm, dets, n = ctx.chain(raw, B)
+        # (a) replicated CPIs give replicated outputs (chunk boundaries fall mid-batch)
+        assert np.array_equal(rdm[0], rdm[2]) and np.array_equal(rdm[1], rdm[7])
+        d0 = key(dets[dets["cpi"] == 0])
+        d6 = key(dets[dets["cpi"] == 6])
+        assert len(d0) == len(d6) and all(np.array_equal(d0[f], d6[f]) for f in ("lane", "v", "r", "kind", "amp"))
+        # (b) exact power-of-two linearity: 2x input -> 2x RDM, identical detections
+        small = (raw[:2] // 4).astype(np.int16)
+        r1, dd1, _ = ctx.chain(small, 2)
+        r2, dd2, _ = ctx.chain((small * 2).astype(np.int16), 2)
+        assert np.array_equal(r2, 2 * r1)
+        k1, k2 = key(dd1), key(dd2)
+        assert all(np.array_equal(k1[f], k2[f]) for f in ("cpi", "lane", "v", "r", "kind"))
+    # (c) chunk size does not change results
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=8) as ctx:
+        rdm8, dets8, _ = ctx.chain(raw, B)
+    assert np.array_equal(rdm8, rdm)
+    a, b = key(dets), key(dets8)
+    assert len(a) == len(b) and all(np.array_equal(a[f], b[f]) for f in a.dtype.names)
+    # (d) impulse response: a unit impulse on every PRT compresses to conj(ref) reversed before the impulse
+    imp = np.zeros((1, P, R, C, 2), dtype=np.int16)
+    imp[0, :, 1000, :, 0] = 1
+    with _chain_ctx(lib, P, R, C, 1, lib.waveforms.segments_single(R, ref), cfar) as ctx:
+        ctx.chain(imp, 1, want_rdm=False)
+        pc = ctx.debug_fetch_pc(0)
+    want = np.zeros(R, dtype=complex)
+    want[1000 - 66:1001] = np.conj(ref[::-1])
+    _close(pc[5, 17], want)
+
+
+def test_chain_detection_overflow_is_reported(lib):
+    P, R, C, B = 64, 512, 2, 1
+    raw = np.zeros((B, P, R, C, 2), dtype=np.int16)             # all-zero RDM: 0 >= 0 flags every cell
+    ref = mcode.load_ref("refDDCDataMF1")
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), synth.cfar_tuple(synth.S3_CFAR), max_det=1000) as ctx:
+        with pytest.raises(lib.DetectionOverflow):
+            ctx.chain(raw, B)
+        rdm, dets, n = ctx.chain(raw, B, allow_overflow=True)
+        assert n > 1000 and len(dets) == 1000
