@@ -201,6 +201,13 @@ int rb200_last_device_ms(const rb200_ctx* ctx, float* ms);
 /* Number of kernels the last call launched (bench.py's gpu_launches).                             */
 int rb200_last_launch_count(const rb200_ctx* ctx, int* n);
 
+/* Per-stage device timing for the roofline report: when on, every chunk of a chain call is bracketed
+ * by CUDA events on the launching stream (before PC, after PC, after MTD, after CFAR).
+ * rb200_get_stage_ms sums the elapsed milliseconds of {PC, MTD, CFAR} over all chunks recorded since
+ * the last call and reports how many chunks / CPIs they covered.                                    */
+int rb200_set_stage_timing(rb200_ctx* ctx, int on);
+int rb200_get_stage_ms(rb200_ctx* ctx, float ms[3], int* n_chunks, int* n_cpis);
+
 /* ---- "next" rows ---------------------------------------------------------*/
 
 /* f1: DBF weighting fused into the unpack: beams = sig_C * W.' (FrameDataRead_xzr.m:158).

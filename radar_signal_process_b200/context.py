@@ -199,6 +199,16 @@ class Context:
         self._ck(self._lib.rb200_last_device_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def set_stage_timing(self, on):
+        self._ck(self._lib.rb200_set_stage_timing(self._h, int(bool(on))))
+
+    def get_stage_ms(self):
+        """({'pc': ms, 'mtd': ms, 'cfar': ms}, n_chunks, n_cpis) accumulated since the last call."""
+        ms = (C.c_float * 3)()
+        nch, ncp = C.c_int(0), C.c_int(0)
+        self._ck(self._lib.rb200_get_stage_ms(self._h, ms, C.byref(nch), C.byref(ncp)))
+        return {"pc": ms[0], "mtd": ms[1], "cfar": ms[2]}, nch.value, ncp.value
+
     def last_launch_count(self):
         n = C.c_int(0)
         self._ck(self._lib.rb200_last_launch_count(self._h, C.byref(n)))

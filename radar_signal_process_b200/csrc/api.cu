@@ -122,6 +122,7 @@ struct Plan {
         taps.release();
         segs.clear();
         out_ranges.clear();
+        max_in_end = max_out_end = 0;
         valid = false;
     }
 };
@@ -156,7 +157,25 @@ struct rb200_ctx {
     // pinned staging for host detections
     rb200_det* h_dets = nullptr;
     int* h_counts = nullptr;
+    // optional per-stage timing (bench.py roofline): 4 events per chunk, consumed by rb200_get_stage_ms
+    bool stage_timing = false;
+    std::vector<cudaEvent_t> stage_events;
+    size_t stage_used = 0;
+    std::vector<int> stage_cpis;       // CPIs per timed chunk
+    int stage_k1_launches = 0;
 };
+
+static cudaEvent_t stage_event(rb200_ctx* c, cudaStream_t st) {
+    if (!c->stage_timing || c->stage_used >= 65536) return nullptr;
+    if (c->stage_used == c->stage_events.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        c->stage_events.push_back(e);
+    }
+    cudaEvent_t e = c->stage_events[c->stage_used++];
+    cudaEventRecord(e, st);
+    return e;
+}
 
 static std::string g_create_error;
 
@@ -531,6 +550,7 @@ extern "C" int rb200_destroy(rb200_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     if (c->h_dets) cudaFreeHost(c->h_dets);
     if (c->h_counts) cudaFreeHost(c->h_counts);
+    for (cudaEvent_t e : c->stage_events) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -923,11 +943,15 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         const int g = std::min(G, n_cpi - c0);
         const int16_t* raw_chunk = raw_dev + (size_t)c0 * cpi_cells * 2;
         float* rdm_chunk = rdm_dev ? rdm_base + (size_t)c0 * cpi_cells : rdm_base;
+        const bool timed = c->stage_timing && c->stage_used + 4 <= 65536;
+        if (timed) { stage_event(c, st); c->stage_cpis.push_back(g); }
         int rc = run_pc(c, c->plan, true, raw_chunk, c->pc.as<float2>(), R, R, C, P, g * P, 0,
                         c->gain_n ? c->gain.as<float>() : nullptr, st);
         if (rc) return rc;
+        if (timed) stage_event(c, st);
         rc = run_mtd(c, c->pc.as<float2>(), rdm_chunk, P, R, R, R, g * C, k.kaiser_beta, k.zero_v_div, k.mti_lag, st);
         if (rc) return rc;
+        if (timed) stage_event(c, st);
         cp.cpi0 = c0;
         if (cp.v_hi > cp.v_lo) {
             // hits of this chunk start where the list currently ends
@@ -937,6 +961,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
                                   c->errflag.as<int>(), st));
             c->launches += cp.range_stage ? 2 : 1;
         }
+        if (timed) stage_event(c, st);
         c->last_chunk_cpis = g;
     }
     CK(c, cudaEventRecord(c->ev1, st));
@@ -1019,6 +1044,36 @@ extern "C" int rb200_last_device_ms(const rb200_ctx* c, float* ms) {
     cudaSetDevice(c->device);
     if (cudaEventSynchronize(c->ev1) != cudaSuccess) return RB200_ERR_CUDA;
     return cudaEventElapsedTime(ms, c->ev0, c->ev1) == cudaSuccess ? RB200_OK : RB200_ERR_CUDA;
+}
+
+extern "C" int rb200_set_stage_timing(rb200_ctx* c, int on) {
+    if (!c) return RB200_ERR_ARG;
+    c->stage_timing = on != 0;
+    c->stage_used = 0;
+    c->stage_cpis.clear();
+    return RB200_OK;
+}
+
+extern "C" int rb200_get_stage_ms(rb200_ctx* c, float ms[3], int* n_chunks, int* n_cpis) {
+    if (!c || !ms) return RB200_ERR_ARG;
+    cudaSetDevice(c->device);
+    ms[0] = ms[1] = ms[2] = 0.f;
+    int chunks = 0, cpis = 0;
+    for (size_t i = 0; i + 3 < c->stage_used; i += 4) {
+        if (cudaEventSynchronize(c->stage_events[i + 3]) != cudaSuccess) return RB200_ERR_CUDA;
+        for (int k = 0; k < 3; ++k) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, c->stage_events[i + k], c->stage_events[i + k + 1]) != cudaSuccess) return RB200_ERR_CUDA;
+            ms[k] += t;
+        }
+        cpis += c->stage_cpis[chunks];
+        ++chunks;
+    }
+    if (n_chunks) *n_chunks = chunks;
+    if (n_cpis) *n_cpis = cpis;
+    c->stage_used = 0;
+    c->stage_cpis.clear();
+    return RB200_OK;
 }
 
 extern "C" int rb200_last_launch_count(const rb200_ctx* c, int* n) {

@@ -85,3 +85,8 @@ def segments_mtd(n, pulse2, pulse3, p1, p2, p3):
 def segments_single(n, ref):
     """One matched-filter segment over the whole PRT (benchmark plan 'single')."""
     return [_seg(0, n, 0, n, SEG_MF, ALIGN_LEADING_EDGE, ref)]
+
+# MP/refDDCDataMF1.mat / MP/refDBFDataMF1.mat (variable refData, 67 taps; load sites
+# CW/DMX_SignalProcessing_main_xzr.m:157-159)
+REF_DDC = np.array(_literals.REF_DDC_REAL, dtype=np.float64) + 1j * np.array(_literals.REF_DDC_IMAG, dtype=np.float64)
+REF_DBF = np.array(_literals.REF_DBF_REAL, dtype=np.float64) + 1j * np.array(_literals.REF_DBF_IMAG, dtype=np.float64)
