@@ -130,6 +130,7 @@ struct Plan {
 struct MtdPlan {
     int P = 0;
     double beta = 0;
+    std::vector<float> h_window;
     DevBuf window, tw;
     int n_stages = 0;
     int radix[16];
@@ -147,7 +148,8 @@ struct rb200_ctx {
     DevBuf gain;
     int gain_n = 0;
     // chain buffers
-    DevBuf raw, pc, rdm, dets_v, dets_2d, counters, vmask, errflag;
+    DevBuf raw, pc, rdm, dets_v, dets_2d, counters, vmask, errflag, colmask;
+    int n_sms = 148;
     // MATLAB-layout scratch
     DevBuf s_in_re, s_in_im, s_a, s_b, s_c, s_out_re, s_out_im, s_u8a, s_u8b, s_idx;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -324,11 +326,8 @@ static int build_plan(rb200_ctx* ctx, Plan& plan, const rb200_segment* segs, int
         c.n_tiles = (int)tiles.size();
         CK(ctx, c.tiles.ensure(tiles.size() * sizeof(int2)));
         CK(ctx, cudaMemcpyAsync(c.tiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-        std::vector<float2> tw(c.nt);
-        for (int m = 0; m < c.nt; ++m) {
-            const double a = -2.0 * M_PI * m / c.nt;
-            tw[m] = make_float2((float)std::cos(a), (float)std::sin(a));
-        }
+        std::vector<float2> tw;
+        pc_build_twiddles(c.nt, tw);
         CK(ctx, c.tw.ensure(tw.size() * sizeof(float2)));
         CK(ctx, cudaMemcpyAsync(c.tw.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
     }
@@ -406,6 +405,7 @@ static int get_mtd_plan(rb200_ctx* ctx, int P, double beta, MtdPlan** out) {
     std::vector<double> w = kaiser_window(P, beta);
     std::vector<float> wf(P);
     for (int i = 0; i < P; ++i) wf[i] = (float)w[i];
+    mp->h_window = wf;
     std::vector<float2> tw(P);
     for (int m = 0; m < P; ++m) {
         const double a = -2.0 * M_PI * m / P;
@@ -520,6 +520,7 @@ extern "C" int rb200_create(rb200_ctx** out, int device, const rb200_config* cfg
         return RB200_ERR_ARG;
     }
     if (validate_cfar(c, k)) { g_create_error = c->err; delete c; return RB200_ERR_ARG; }
+    cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device);
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
@@ -545,7 +546,7 @@ extern "C" int rb200_destroy(rb200_ctx* c) {
         kv.second->tw.release();
         delete kv.second;
     }
-    DevBuf* bufs[] = {&c->gain, &c->raw, &c->pc, &c->rdm, &c->dets_v, &c->dets_2d, &c->counters, &c->vmask, &c->errflag,
+    DevBuf* bufs[] = {&c->gain, &c->raw, &c->pc, &c->rdm, &c->dets_v, &c->dets_2d, &c->counters, &c->vmask, &c->errflag, &c->colmask,
                       &c->s_in_re, &c->s_in_im, &c->s_a, &c->s_b, &c->s_c, &c->s_out_re, &c->s_out_im, &c->s_u8a, &c->s_u8b, &c->s_idx};
     for (DevBuf* b : bufs) b->release();
     if (c->h_dets) cudaFreeHost(c->h_dets);
@@ -938,6 +939,31 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     c->launches = 0;
     CK(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(int), st));
     CK(c, cudaMemsetAsync(c->errflag.p, 0, sizeof(int), st));
+    const bool fused = !getenv("RB200_NO_FUSED") && mtd64_fused_supported(P, k.cfar_ref_v, k.cfar_guard_v, k.cfar_n0, k.mti_lag);
+    Mtd64Params m64;
+    memset(&m64, 0, sizeof m64);
+    if (fused) {
+        MtdPlan* mp = nullptr;
+        int rc = get_mtd_plan(c, P, k.kaiser_beta, &mp);
+        if (rc) return rc;
+        int zlo, zhi;
+        if (zero_v_rows(P, k.zero_v_div, &zlo, &zhi)) return fail(c, RB200_ERR_INDEX, "fun_0v_pressing: Index in position 1 is invalid");
+        for (int i = 0; i < 64; ++i) {
+            m64.win[i] = mp->h_window[i];
+            m64.keep[i] = (i >= zlo && i <= zhi) ? 0.f : 1.f;
+        }
+        m64.in_ld = m64.out_ld = m64.cols = R;
+        m64.meth_v = k.cfar_method_v;
+        m64.tv_over_ref = (float)(k.cfar_t_v / k.cfar_ref_v);
+        m64.dets = c->dets_v.p;
+        m64.det_count = c->counters.as<int>();
+        CK(c, c->colmask.ensure((size_t)G * C * R * sizeof(unsigned long long)));
+        m64.colmask = c->colmask.as<unsigned long long>();
+        m64.cols_ld = R;
+        m64.max_det = k.max_det;
+        m64.n_lanes = C;
+    }
+    int chunk_idx = 0;
     CK(c, cudaEventRecord(c->ev0, st));
     for (int c0 = 0; c0 < n_cpi; c0 += G) {
         const int g = std::min(G, n_cpi - c0);
@@ -949,18 +975,34 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
                         c->gain_n ? c->gain.as<float>() : nullptr, st);
         if (rc) return rc;
         if (timed) stage_event(c, st);
-        rc = run_mtd(c, c->pc.as<float2>(), rdm_chunk, P, R, R, R, g * C, k.kaiser_beta, k.zero_v_div, k.mti_lag, st);
-        if (rc) return rc;
-        if (timed) stage_event(c, st);
         cp.cpi0 = c0;
-        if (cp.v_hi > cp.v_lo) {
-            // hits of this chunk start where the list currently ends
-            CK(c, cudaMemcpyAsync(c->counters.as<int>() + 2, c->counters.as<int>() + 0, sizeof(int), cudaMemcpyDeviceToDevice, st));
-            CK(c, launch_cfar_f32(rdm_chunk, cp, (float)k.cfar_t_r, (float)k.cfar_t_v, g * C, c->dets_v.p, c->counters.as<int>() + 0,
-                                  c->dets_2d.p, c->counters.as<int>() + 1, c->vmask.as<uint32_t>(), nullptr, nullptr,
-                                  c->errflag.as<int>(), st));
-            c->launches += cp.range_stage ? 2 : 1;
+        if (fused) {
+            // K2 + velocity CFAR in one kernel (register-resident Doppler columns), then the sparse range stage
+            m64.in = c->pc.as<float2>();
+            m64.out = rdm_chunk;
+            m64.cpi0 = c0;
+            CK(c, launch_mtd64(m64, g * C, true, st));
+            c->launches++;
+            if (timed) stage_event(c, st);
+            if (cp.range_stage) {
+                CK(c, launch_cfar_r64(rdm_chunk, cp, (float)k.cfar_t_r, c->dets_v.p, c->counters.as<int>(), c->dets_2d.p,
+                                      c->colmask.as<unsigned long long>(), R, chunk_idx & 1, c->errflag.as<int>(), c->n_sms, st));
+                c->launches++;
+            }
+        } else {
+            rc = run_mtd(c, c->pc.as<float2>(), rdm_chunk, P, R, R, R, g * C, k.kaiser_beta, k.zero_v_div, k.mti_lag, st);
+            if (rc) return rc;
+            if (timed) stage_event(c, st);
+            if (cp.v_hi > cp.v_lo) {
+                // hits of this chunk start where the list currently ends
+                CK(c, cudaMemcpyAsync(c->counters.as<int>() + 2, c->counters.as<int>() + 0, sizeof(int), cudaMemcpyDeviceToDevice, st));
+                CK(c, launch_cfar_f32(rdm_chunk, cp, (float)k.cfar_t_r, (float)k.cfar_t_v, g * C, c->dets_v.p, c->counters.as<int>() + 0,
+                                      c->dets_2d.p, c->counters.as<int>() + 1, c->vmask.as<uint32_t>(), nullptr, nullptr,
+                                      c->errflag.as<int>(), st));
+                c->launches += cp.range_stage ? 2 : 1;
+            }
         }
+        ++chunk_idx;
         if (timed) stage_event(c, st);
         c->last_chunk_cpis = g;
     }

@@ -51,6 +51,24 @@ struct MtdParams {
     int radix[16];
 };
 
+struct rb200_det_fwd;
+// P = 64 register-column kernel (mtd64_kernel.cu): window / keep factors travel in the parameter block
+struct Mtd64Params {
+    const float2* in;       // planar [slab][prt][range]
+    float* out;             // [slab][v][range]
+    int in_ld, out_ld, cols;
+    float win[64];          // Kaiser window
+    float keep[64];         // 0 for zero-velocity rows, 1 elsewhere (per output row)
+    // fused velocity-axis CFAR
+    int meth_v;
+    float tv_over_ref;      // T_V / refCells_V
+    void* dets;             // rb200_det list (velocity hits)
+    int* det_count;
+    unsigned long long* colmask;   // [slab][cols_ld]: bit v set = velocity hit at (v, r)
+    int cols_ld;
+    int max_det, n_lanes, cpi0;
+};
+
 struct CfarParams {
     int V, R;               // full RDM size
     int v_lo, v_hi;         // 0-based tested rows [v_lo, v_hi)  (n0+1 .. V-n0)

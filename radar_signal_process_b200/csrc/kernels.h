@@ -2,12 +2,14 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "common.cuh"
 
 namespace rb {
 
 // ---- K1 pulse compression (pc_kernels.cu)
-int pc_tile_lanes(int nt, bool wire);     // lines per CTA for FFT tile size nt (0 = unsupported)
+int pc_tile_lanes(int nt, bool wire);
+void pc_build_twiddles(int nt, std::vector<float2>& tw);   // stage-major twiddle table for tile size nt     // lines per CTA for FFT tile size nt (0 = unsupported)
 cudaError_t launch_pc_fft(int nt, bool wire, const PcParams& p, int n_tiles, int n_groups, cudaStream_t st);
 cudaError_t launch_pc_direct(bool wire, const PcParams& p, const float2* taps, int seg_idx, int out_len, int n_lines, cudaStream_t st);
 cudaError_t launch_pc_zero_cols(float2* out, size_t n_lines, int R, int c0, int c1, cudaStream_t st);
@@ -17,6 +19,12 @@ cudaError_t launch_unpack(const int16_t* raw, float2* out, int n_groups, int P, 
 bool mtd_has_fast_path(int P);
 cudaError_t launch_mtd(const MtdParams& p, int n_slabs, cudaStream_t st);
 int mtd_generic_max_p();
+
+// ---- K2 for P = 64 fused with the velocity CFAR stage, and its sparse range stage (mtd64_kernel.cu)
+bool mtd64_fused_supported(int P, int ref_v, int guard_v, int n0, int mti_lag);
+cudaError_t launch_mtd64(const Mtd64Params& p, int n_slabs, bool with_cfar, cudaStream_t st);
+cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, const void* dets_v, int* counters, void* dets_2d,
+                            const unsigned long long* colmask, int cols_ld, int chunk_parity, int* err_flag, int n_sms, cudaStream_t st);
 
 // ---- K3 CFAR (cfar_kernels.cu)
 // chain variant: float RDM [slab][V][R] row-major -> velocity-hit list + 2-D list (+ optional dense uint8 flags)

@@ -1,0 +1,242 @@
+// mtd64_kernel.cu -- K2 for P = 64: Kaiser window + 64-point slow-time FFT + fftshift + |.| + zero-velocity
+// mask, fused with the velocity-axis CA-CFAR stage and its detection compaction.
+//
+// Replaces the per-range-cell loop of MP/fun_Process_MTD.m:20-30, MP/fun_0v_pressing.m:4-6 and the
+// velocity stage of CW/executeCFAR.m:28 (CW/Function_CFAR1D_sub.m:17-69).
+//
+// One thread owns one range cell of one slab and keeps its whole 64-sample Doppler column in
+// registers (64 complex = 128 registers; B200 has 64 K registers per SM):
+//   * 64 loads of 8 B, each warp-coalesced along range (256 B per warp per PRT row);
+//   * window weights and the zero-velocity keep factors come from the kernel parameter block
+//     (constant bank operands, no loads);
+//   * the 64-point FFT is 8 x radix-8, compile-time twiddles (immediates), 8 x radix-8 -- no shared
+//     memory, no barriers;
+//   * fftshift is output indexing; magnitudes are stored range-contiguous (128 B per warp per row);
+//   * the velocity CFAR runs on the magnitudes still in registers: a register prefix sum gives every
+//     window sum with two subtractions; edge substitution and the tested-row crop are resolved at
+//     compile time for the (ref, guard, n0) specialisation;
+//   * per column the 64 hit bits are stored as one 8-byte word (consumed by the range stage for
+//     de-duplication) and hits are appended to the detection list with one atomic per warp.
+#include "common.cuh"
+#include "radix.cuh"
+#include "tw64.cuh"
+#include "kernels.h"
+#include "../../include/radar_b200.h"
+
+namespace rb {
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <int REF, int GUARD, int N0, bool CFAR>
+__global__ void __launch_bounds__(128)
+mtd64_kernel(const Mtd64Params p) {
+    constexpr int P = 64;
+    const int slab = blockIdx.y;
+    const int r = blockIdx.x * 128 + threadIdx.x;
+    const bool ok = r < p.cols;
+    const int rc = ok ? r : p.cols - 1;      // clamp: inactive threads still take part in warp votes
+    const float2* col = p.in + (size_t)slab * P * p.in_ld + rc;
+
+    float2 v[P];
+#pragma unroll
+    for (int prt = 0; prt < P; ++prt) {
+        const float2 x = __ldg(col + (size_t)prt * p.in_ld);
+        v[prt] = make_float2(x.x * p.win[prt], x.y * p.win[prt]);
+    }
+    // ---- 64-point DIF: step 1, radix-8 over j for every q (elements q + 8j), twiddle w64^(q*k0) ----
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float2 a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = v[q + 8 * j];
+        dft8<-1>(a);
+#pragma unroll
+        for (int k0 = 0; k0 < 8; ++k0) {
+            const int m = (q * k0) & 63;
+            v[q + 8 * k0] = (m == 0) ? a[k0] : cmul(a[k0], make_float2(kCos64[m], -kSin64[m]));
+        }
+    }
+    // ---- step 2: radix-8 over q for every k0 (elements 8*k0 .. 8*k0+7) -> X[k0 + 8*k1] at 8*k0 + k1 ----
+    float mag[P];   // indexed by output row (fftshifted)
+#pragma unroll
+    for (int k0 = 0; k0 < 8; ++k0) {
+        float2 a[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] = v[q + 8 * k0];
+        dft8<-1>(a);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) {
+            const int row = (k0 + 8 * k1 + P / 2) & (P - 1);
+            mag[row] = fast_sqrt(a[k1].x * a[k1].x + a[k1].y * a[k1].y) * p.keep[row];
+        }
+    }
+    if (ok) {
+        float* out = p.out + (size_t)slab * P * p.out_ld + r;
+#pragma unroll
+        for (int row = 0; row < P; ++row) out[(size_t)row * p.out_ld] = mag[row];
+    }
+    if (!CFAR) return;
+
+    // ---- velocity-axis CA-CFAR on the register column (tested rows N0+1 .. 63-N0) ----
+    constexpr int NV = P - 2 * N0 - 1;
+    static_assert(!CFAR || NV >= 2 * (REF + GUARD), "velocity axis shorter than 2*(ref+guard)");
+    float pre[NV + 1];
+    pre[0] = 0.f;
+#pragma unroll
+    for (int y = 0; y < NV; ++y) pre[y + 1] = pre[y] + mag[N0 + 1 + y];
+    unsigned long long hits = 0ull;
+#pragma unroll
+    for (int y = 0; y < NV; ++y) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int l1 = y - GUARD - REF;
+        const int r2 = y + GUARD + REF;
+        const bool okL = l1 >= 0;
+        const bool okR = r2 <= NV - 1;
+        const float sl = okL ? pre[y - GUARD] - pre[okL ? l1 : 0] : 0.f;
+        const float sr = okR ? pre[okR ? r2 + 1 : 0] - pre[okR ? y + GUARD + 1 : 0] : 0.f;
+        const float a = okL ? sl : sr;
+        const float b = okR ? sr : sl;
+        const float mu = p.meth_v == 0 ? fmaxf(a, b) : fminf(a, b);
+        if (mag[N0 + 1 + y] >= mu * p.tv_over_ref) hits |= 1ull << (N0 + 1 + y);
+    }
+    if (!ok) hits = 0ull;
+    if (ok) p.colmask[(size_t)slab * p.cols_ld + r] = hits;
+    // ---- compaction: one atomic per warp ----
+    if (!__any_sync(0xffffffffu, hits != 0ull)) return;
+    const int lane = threadIdx.x & 31;
+    const int n = __popcll(hits);
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31) base = atomicAdd(p.det_count, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int slot = base + incl - n;
+    unsigned long long h = hits;
+    while (h) {
+        const int row = __ffsll((long long)h) - 1;
+        h &= h - 1;
+        if (slot < p.max_det) {
+            rb200_det d;
+            d.cpi = (uint32_t)(p.cpi0 + slab / p.n_lanes);
+            d.r = (uint32_t)r;
+            d.v = (uint16_t)row;
+            d.lane = (uint8_t)(slab % p.n_lanes);
+            d.kind = RB200_DET_V;
+            // mag[] is register-resident with static indexing only: re-read the stored magnitude
+            d.amp = p.out[((size_t)slab * P + row) * p.out_ld + r];
+            reinterpret_cast<rb200_det*>(p.dets)[slot] = d;
+        }
+        ++slot;
+    }
+}
+
+// Range stage for the fused path: one (grid-stride) thread per velocity hit; same election rule as
+// cfar_r_kernel but the velocity-hit membership test reads the per-column 64-bit masks.
+__global__ void cfar_r64_kernel(const float* __restrict__ rdm, const CfarParams p, float t_r,
+                                const rb200_det* __restrict__ dets_v, int* __restrict__ counters,
+                                rb200_det* __restrict__ dets_2d, const unsigned long long* __restrict__ colmask,
+                                int cols_ld, int chunk_parity, int* err_flag);
+
+__device__ __forceinline__ bool cfar_decide_f32(const float* __restrict__ row, int y, int N, int ref, int guard, float thr, int method, int* err_flag) {
+    const int l1 = y - guard - ref;
+    const int r1 = y + guard + 1;
+    const bool okL = l1 >= 0;
+    const bool okR = (y + guard + ref) <= N - 1;
+    if (!okL && !okR) {
+        if (err_flag) *err_flag = 1;
+        return false;
+    }
+    float sl = 0.f, sr = 0.f;
+    if (okL) for (int j = 0; j < ref; ++j) sl += row[l1 + j];
+    if (okR) for (int j = 0; j < ref; ++j) sr += row[r1 + j];
+    const float mr = sr / (float)ref, ml = sl / (float)ref;
+    const float a = okL ? ml : mr;
+    const float b = okR ? mr : ml;
+    const float mu = method == 0 ? fmaxf(a, b) : fminf(a, b);
+    return row[y] >= mu * thr;
+}
+
+__device__ __forceinline__ int cfar_elect_f32(const float* __restrict__ row, int r, const CfarParams& p, float t_r, int* err_flag) {
+    int best = -1;
+    float bestv = 0.f;
+#pragma unroll
+    for (int d = -1; d <= 1; ++d) {
+        const int c = r + d;
+        if (c < 0 || c >= p.R) continue;
+        if (!cfar_decide_f32(row, c, p.R, p.ref_r, p.guard_r, t_r, p.meth_r, err_flag)) continue;
+        const float x = row[c];
+        if (best < 0 || x > bestv) { best = c; bestv = x; }
+    }
+    return best;
+}
+
+__global__ void cfar_r64_kernel(const float* __restrict__ rdm, const CfarParams p, float t_r,
+                                const rb200_det* __restrict__ dets_v, int* __restrict__ counters,
+                                rb200_det* __restrict__ dets_2d, const unsigned long long* __restrict__ colmask,
+                                int cols_ld, int chunk_parity, int* err_flag) {
+    // counters: [0] velocity hits so far, [1] 2-D records so far, [2 + parity] first hit of this chunk.
+    const int start = counters[2 + chunk_parity];
+    int n = counters[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[2 + (chunk_parity ^ 1)] = n;   // next chunk starts here
+    if (n > p.max_det) n = p.max_det;
+    for (int i = start + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const rb200_det h = dets_v[i];
+        const int slab = (int)(h.cpi - p.cpi0) * p.n_lanes + h.lane;
+        const int v = h.v, r = (int)h.r;
+        const float* row = rdm + ((size_t)slab * p.V + v) * p.R;
+        const int c = cfar_elect_f32(row, r, p, t_r, err_flag);
+        if (c < 0) continue;
+        const unsigned long long* cm = colmask + (size_t)slab * cols_ld;
+        bool owner = true;
+        for (int rr = c - 1; rr < r && owner; ++rr) {
+            if (rr < 0) continue;
+            if (!((cm[rr] >> v) & 1ull)) continue;
+            if (cfar_elect_f32(row, rr, p, t_r, nullptr) == c) owner = false;
+        }
+        if (!owner) continue;
+        const int slot = atomicAdd(&counters[1], 1);
+        if (slot < p.max_det) {
+            rb200_det d;
+            d.cpi = h.cpi;
+            d.r = (uint32_t)c;
+            d.v = h.v;
+            d.lane = h.lane;
+            d.kind = RB200_DET_2D;
+            d.amp = row[c];
+            dets_2d[slot] = d;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+bool mtd64_fused_supported(int P, int ref_v, int guard_v, int n0, int mti_lag) {
+    return P == 64 && ref_v == 5 && guard_v == 7 && n0 == 0 && mti_lag == 0;
+}
+
+cudaError_t launch_mtd64(const Mtd64Params& p, int n_slabs, bool with_cfar, cudaStream_t st) {
+    if (p.cols <= 0 || n_slabs <= 0) return cudaSuccess;
+    dim3 grid((p.cols + 127) / 128, n_slabs, 1);
+    if (n_slabs > 65535) return cudaErrorInvalidConfiguration;
+    if (with_cfar) mtd64_kernel<5, 7, 0, true><<<grid, 128, 0, st>>>(p);
+    else mtd64_kernel<5, 7, 0, false><<<grid, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, const void* dets_v, int* counters, void* dets_2d,
+                            const unsigned long long* colmask, int cols_ld, int chunk_parity, int* err_flag, int n_sms, cudaStream_t st) {
+    cfar_r64_kernel<<<n_sms * 2, 128, 0, st>>>(rdm, p, t_r, (const rb200_det*)dets_v, counters, (rb200_det*)dets_2d, colmask, cols_ld,
+                                               chunk_parity, err_flag);
+    return cudaGetLastError();
+}
+
+}  // namespace rb

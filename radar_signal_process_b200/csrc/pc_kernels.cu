@@ -24,11 +24,23 @@
 #include "common.cuh"
 #include "radix.cuh"
 #include "kernels.h"
+#include <cmath>
+#include <vector>
 
 namespace rb {
 
-template <int R, int S, int LT, bool WIRE>
-__global__ void __launch_bounds__(LT * (ipow(R, S) / R))
+// offset (in float2) of the stage-s twiddle block inside PcParams::tw:  T_s[k*st_s + q] = w_NT^(q*k*R^s),
+// st_s = NT / R^(s+1).  Blocks exist for s = 0 .. S-2 (the last stage has no twiddles).
+template <int R, int S> __host__ __device__ constexpr int tw_block_off(int s) {
+    int off = 0;
+    for (int i = 0; i < s; ++i) off += R * (ipow(R, S) / ipow(R, i + 1));
+    return off;
+}
+
+template <int R, int S, int LT> struct PcOcc { static constexpr int min_blocks = (LT * (ipow(R, S) / R) <= 256) ? 3 : 1; };
+
+template <int R, int S, int LT, bool WIRE, int CFIX>
+__global__ void __launch_bounds__(LT * (ipow(R, S) / R), PcOcc<R, S, LT>::min_blocks)
 pc_fft_kernel(const PcParams p) {
     constexpr int NT = ipow(R, S);
     constexpr int NB = NT / R;     // butterflies per line per stage
@@ -42,37 +54,65 @@ pc_fft_kernel(const PcParams p) {
     const PcSegDev& sg = p.segs[tile.x];
     const int g = blockIdx.x;
     const int in_off = tile.y * sg.V - sg.pre;
+    const int C = CFIX > 0 ? CFIX : p.C;
 
     float2 v[R];
     // ---- stage 0 operands straight from global memory (unpack fused) ----
     {
-        bool lane_ok;
-        size_t base;
         const int lane_g = blockIdx.z * LT + lane;   // wire: channel index
+        bool lane_ok;
+        long long e0;        // index of the element (range = in_start + in_off + u) of this line
+        int es;              // element stride between consecutive range cells
         if (WIRE) {
-            lane_ok = lane_g < p.C;
-            base = (size_t)g * p.R;
+            lane_ok = lane_g < C;
+            e0 = ((long long)g * p.R + sg.in_start + in_off + u) * C + lane_g;
+            es = C;
         } else {
             const int line = g * LT + lane;
             lane_ok = line < p.n_lines;
-            base = (size_t)line * p.R;
+            e0 = (long long)line * p.R + sg.in_start + in_off + u;
+            es = 1;
         }
+        const bool interior = in_off >= 0 && in_off + NT <= sg.in_len;   // CTA-uniform
+        if (interior && lane_ok) {
+            if (WIRE) {
+                const int* src = reinterpret_cast<const int*>(p.in) + e0;
+                int w[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-            const int rs = in_off + u + j * NB;
-            float2 x = make_float2(0.f, 0.f);
-            if (lane_ok && rs >= 0 && rs < sg.in_len) {
-                const int r = sg.in_start + rs;
-                if (WIRE) {
-                    const int w = __ldg(reinterpret_cast<const int*>(p.in) + (base + r) * p.C + lane_g);
-                    x.x = (float)(short)(w & 0xffff);   // I  (little-endian int16 pair, FrameDataRead_xzr.m:154)
-                    x.y = (float)(short)(w >> 16);      // Q  (:155)
-                } else {
-                    x = __ldg(reinterpret_cast<const float2*>(p.in) + base + r);
+                for (int j = 0; j < R; ++j) w[j] = __ldg(src + (long long)j * NB * es);
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    v[j].x = (float)(short)(w[j] & 0xffff);   // I (FrameDataRead_xzr.m:154)
+                    v[j].y = (float)(w[j] >> 16);             // Q (:155)
                 }
-                if (p.gain) x = cscale(x, __ldg(p.gain + r));
+            } else {
+                const float2* src = reinterpret_cast<const float2*>(p.in) + e0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) v[j] = __ldg(src + j * NB);
             }
-            v[j] = x;
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int rs = in_off + u + j * NB;
+                float2 x = make_float2(0.f, 0.f);
+                if (lane_ok && rs >= 0 && rs < sg.in_len) {
+                    if (WIRE) {
+                        const int w = __ldg(reinterpret_cast<const int*>(p.in) + e0 + (long long)j * NB * es);
+                        x.x = (float)(short)(w & 0xffff);
+                        x.y = (float)(w >> 16);
+                    } else {
+                        x = __ldg(reinterpret_cast<const float2*>(p.in) + e0 + j * NB);
+                    }
+                }
+                v[j] = x;
+            }
+        }
+        if (p.gain) {      // iSTC (MP/fun_iSTC.m:14): per-range gain before compression
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int rs = in_off + u + j * NB;
+                if (rs >= 0 && rs < sg.in_len) v[j] = cscale(v[j], __ldg(p.gain + sg.in_start + rs));
+            }
         }
     }
     float2* line_sm = sm + lane * LS;
@@ -80,8 +120,9 @@ pc_fft_kernel(const PcParams p) {
     // ---- forward DIF ----
     Dft<R, -1>::run(v);
     if (S > 1) {
+        const float2* tw = p.tw + u;      // stage-0 block: T[k*NB + u]
 #pragma unroll
-        for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(p.tw + u * k));
+        for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(tw + k * NB));
     }
 #pragma unroll
     for (int s = 1; s < S; ++s) {
@@ -97,9 +138,9 @@ pc_fft_kernel(const PcParams p) {
         for (int j = 0; j < R; ++j) v[j] = line_sm[base + j * st];
         Dft<R, -1>::run(v);
         if (st > 1) {
-            const int m = q * ipow(R, s);
+            const float2* tw = p.tw + tw_block_off<R, S>(s) + q;
 #pragma unroll
-            for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(p.tw + m * k));
+            for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(tw + k * st));
         }
     }
 
@@ -121,14 +162,15 @@ pc_fft_kernel(const PcParams p) {
         const int st = NT / ipow(R, s + 1);
         const int q = u % st;
         if (st > 1 && s > 0) {
-            const int m = q * ipow(R, s);
+            const float2* tw = p.tw + tw_block_off<R, S>(s) + q;
 #pragma unroll
-            for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], __ldg(p.tw + m * k));
+            for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], __ldg(tw + k * st));
         }
         if (s == 0 && S > 1) {
             // stage-0 operands were fetched with the store mapping (out_lane, out_u)
+            const float2* tw = p.tw + out_u;
 #pragma unroll
-            for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], __ldg(p.tw + out_u * k));
+            for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], __ldg(tw + k * NB));
         }
         Dft<R, +1>::run(v);
         if (s > 0) {
@@ -159,24 +201,32 @@ pc_fft_kernel(const PcParams p) {
         if (WIRE) {
             const int cpi = g / p.P, prt = g % p.P;
             const int out_lane_g = blockIdx.z * LT + out_lane;
-            ok = out_lane_g < p.C;
-            oline = ((size_t)cpi * p.C + out_lane_g) * p.P + prt;
+            ok = out_lane_g < C;
+            oline = ((size_t)cpi * C + out_lane_g) * p.P + prt;
         } else {
             const int line = g * LT + out_lane;
             ok = line < p.n_lines;
             oline = line;
         }
         if (ok) {
-            float2* o = p.out + oline * p.R_out + sg.out_start;
             const int n0 = tile.y * sg.V;
+            float2* o = p.out + oline * p.R_out + sg.out_start;
+            if (sg.rot == 0) {
+                const int lim = min(sg.V, sg.out_len - n0);    // valid lags of this tile
+                o += n0 + out_u;
 #pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const int nl = out_u + j * NB;
-                const int n = n0 + nl;
-                if (nl < sg.V && n < sg.out_len) {
-                    int c = n - sg.rot;
-                    if (c < 0) c += sg.out_len;
-                    o[c] = v[j];
+                for (int j = 0; j < R; ++j)
+                    if (out_u + j * NB < lim) o[j * NB] = v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int nl = out_u + j * NB;
+                    const int n = n0 + nl;
+                    if (nl < sg.V && n < sg.out_len) {
+                        int c = n - sg.rot;
+                        if (c < 0) c += sg.out_len;
+                        o[c] = v[j];
+                    }
                 }
             }
         }
@@ -253,21 +303,40 @@ __global__ void unpack_kernel(const int* __restrict__ raw, float2* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-template <int R, int S, int LT, bool WIRE>
+template <int R, int S, int LT, bool WIRE, int CFIX>
 static cudaError_t launch_fft(const PcParams& p, int n_tiles, int n_groups, cudaStream_t st) {
     constexpr int NT = ipow(R, S);
     constexpr int threads = LT * (NT / R);
     const size_t smem = (size_t)LT * (NT + 1) * sizeof(float2);
-    static bool configured = false;
+    static bool configured = false;   // per template instantiation
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(pc_fft_kernel<R, S, LT, WIRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(pc_fft_kernel<R, S, LT, WIRE, CFIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     dim3 grid(n_groups, n_tiles, WIRE ? (p.C + LT - 1) / LT : 1);
     if (n_tiles > 65535) return cudaErrorInvalidConfiguration;
-    pc_fft_kernel<R, S, LT, WIRE><<<grid, threads, smem, st>>>(p);
+    pc_fft_kernel<R, S, LT, WIRE, CFIX><<<grid, threads, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+// Host: stage-major twiddle table consumed by pc_fft_kernel (see tw_block_off).
+void pc_build_twiddles(int nt, std::vector<float2>& tw) {
+    const int R = (nt == 512) ? 8 : 16;
+    int S = 0;
+    for (int n = nt; n > 1; n /= R) ++S;
+    tw.clear();
+    int Rs = 1;                                   // R^s
+    for (int s = 0; s + 1 < S; ++s) {
+        const int st = nt / (Rs * R);
+        for (int k = 0; k < R; ++k)
+            for (int q = 0; q < st; ++q) {
+                const double a = -2.0 * M_PI * (double)(((long long)q * k * Rs) % nt) / (double)nt;
+                tw.push_back(make_float2((float)cos(a), (float)sin(a)));
+            }
+        Rs *= R;
+    }
+    if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
 }
 
 int pc_tile_lanes(int nt, bool wire) {
@@ -281,9 +350,15 @@ int pc_tile_lanes(int nt, bool wire) {
 }
 
 cudaError_t launch_pc_fft(int nt, bool wire, const PcParams& p, int n_tiles, int n_groups, cudaStream_t st) {
-    if (nt == 256) return wire ? launch_fft<16, 2, 16, true>(p, n_tiles, n_groups, st) : launch_fft<16, 2, 16, false>(p, n_tiles, n_groups, st);
-    if (nt == 512) return wire ? launch_fft<8, 3, 16, true>(p, n_tiles, n_groups, st) : launch_fft<8, 3, 16, false>(p, n_tiles, n_groups, st);
-    if (nt == 4096) return wire ? launch_fft<16, 3, 2, true>(p, n_tiles, n_groups, st) : launch_fft<16, 3, 2, false>(p, n_tiles, n_groups, st);
+    if (nt == 256) {
+        if (!wire) return launch_fft<16, 2, 16, false, 0>(p, n_tiles, n_groups, st);
+        return p.C == 16 ? launch_fft<16, 2, 16, true, 16>(p, n_tiles, n_groups, st) : launch_fft<16, 2, 16, true, 0>(p, n_tiles, n_groups, st);
+    }
+    if (nt == 512) {
+        if (!wire) return launch_fft<8, 3, 16, false, 0>(p, n_tiles, n_groups, st);
+        return p.C == 16 ? launch_fft<8, 3, 16, true, 16>(p, n_tiles, n_groups, st) : launch_fft<8, 3, 16, true, 0>(p, n_tiles, n_groups, st);
+    }
+    if (nt == 4096) return wire ? launch_fft<16, 3, 2, true, 0>(p, n_tiles, n_groups, st) : launch_fft<16, 3, 2, false, 0>(p, n_tiles, n_groups, st);
     return cudaErrorInvalidValue;
 }
 
