@@ -193,7 +193,6 @@ def run_gpu(args):
     if sampler:
         sampler.start()
         time.sleep(0.25)
-    ctx.set_stage_timing(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -203,9 +202,21 @@ def run_gpu(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches_per_step = ctx.last_launch_count()
+    dets, n_det = ctx.chain_fetch(allow_overflow=True)
+    # per-kernel durations for the roofline object: the same K steps again with CUDA events around every
+    # stage of every chunk (chunks serialised on one stream; the headline `value` above is measured without
+    # these events and with chunk pipelining on)
+    ctx.set_stage_timing(True)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    s1.record(stream)
+    barrier()
+    ms_serial = s0.elapsed_time(s1)
     stage_ms, n_chunks, n_stage_cpis = ctx.get_stage_ms()
     ctx.set_stage_timing(False)
-    dets, n_det = ctx.chain_fetch(allow_overflow=True)
 
     # ---- end-to-end through the C ABI with pinned host buffers ------------------------------------
     dets_pin = torch.empty(args.max_det * 16, dtype=torch.uint8).pin_memory()
@@ -267,6 +278,7 @@ def run_gpu(args):
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_CPI * cpis_per_launch,
                          "ms_per_launch": pc_ms_per_launch,
+                         "serialised_ms_per_step": ms_serial / args.steps,
                          "stage_share": {k: (v / stage_total if stage_total else None) for k, v in stage_ms.items()},
                          "stage_us_per_cpi": {k: 1e3 * v / max(n_stage_cpis, 1) for k, v in stage_ms.items()}},
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "CPI/s", "h2d_bytes_per_step": B * CELLS * 4,

@@ -150,6 +150,17 @@ struct rb200_ctx {
     // chain buffers
     DevBuf raw, pc, rdm, dets_v, dets_2d, counters, vmask, errflag, colmask;
     int n_sms = 148;
+    // chunk pipelining of the fused path: chunk i runs on slot i % n_slots (own stream + scratch), so the
+    // tail of one chunk's kernels overlaps the head of the next while the PC intermediate stays L2-sized
+    struct Slot {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        DevBuf pc, colmask, vlist, count;
+    };
+    static const int kMaxSlots = 4;
+    Slot slots[kMaxSlots];
+    cudaEvent_t fork_ev = nullptr;
+    const float2* last_pc = nullptr;
     // MATLAB-layout scratch
     DevBuf s_in_re, s_in_im, s_a, s_b, s_c, s_out_re, s_out_im, s_u8a, s_u8b, s_idx;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -525,6 +536,13 @@ extern "C" int rb200_create(rb200_ctx** out, int device, const rb200_config* cfg
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = c->counters.ensure(4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming);
+    for (int i = 0; i < rb200_ctx::kMaxSlots && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&c->slots[i].stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->slots[i].done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = c->slots[i].count.ensure(2 * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(c->slots[i].count.p, 0, 2 * sizeof(int));
+    }
     if (e == cudaSuccess) e = c->errflag.ensure(sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_counts, 4 * sizeof(int));
     if (e != cudaSuccess) {
@@ -551,6 +569,14 @@ extern "C" int rb200_destroy(rb200_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     if (c->h_dets) cudaFreeHost(c->h_dets);
     if (c->h_counts) cudaFreeHost(c->h_counts);
+    for (int i = 0; i < rb200_ctx::kMaxSlots; ++i) {
+        rb200_ctx::Slot& sl = c->slots[i];
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        sl.pc.release(); sl.colmask.release(); sl.vlist.release(); sl.count.release();
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     for (cudaEvent_t e : c->stage_events) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -918,10 +944,8 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     const int G = chunk_size(c);
     const size_t cpi_cells = (size_t)P * R * C;
     const int Rw = (R + 31) / 32;
-    CK(c, c->pc.ensure((size_t)G * cpi_cells * sizeof(float2)));
     CK(c, c->dets_v.ensure((size_t)k.max_det * sizeof(rb200_det)));
     CK(c, c->dets_2d.ensure((size_t)k.max_det * sizeof(rb200_det)));
-    CK(c, c->vmask.ensure((size_t)G * C * P * Rw * sizeof(uint32_t)));
     float* rdm_base = rdm_dev;
     if (!rdm_base) {
         CK(c, c->rdm.ensure((size_t)G * cpi_cells * sizeof(float)));
@@ -942,6 +966,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     const bool fused = !getenv("RB200_NO_FUSED") && mtd64_fused_supported(P, k.cfar_ref_v, k.cfar_guard_v, k.cfar_n0, k.mti_lag);
     Mtd64Params m64;
     memset(&m64, 0, sizeof m64);
+    int n_slots = 1;
     if (fused) {
         MtdPlan* mp = nullptr;
         int rc = get_mtd_plan(c, P, k.kaiser_beta, &mp);
@@ -955,56 +980,79 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         m64.in_ld = m64.out_ld = m64.cols = R;
         m64.meth_v = k.cfar_method_v;
         m64.tv_over_ref = (float)(k.cfar_t_v / k.cfar_ref_v);
-        m64.dets = c->dets_v.p;
-        m64.det_count = c->counters.as<int>();
-        CK(c, c->colmask.ensure((size_t)G * C * R * sizeof(unsigned long long)));
-        m64.colmask = c->colmask.as<unsigned long long>();
         m64.cols_ld = R;
         m64.max_det = k.max_det;
         m64.n_lanes = C;
+        const char* env = getenv("RB200_SLOTS");
+        n_slots = env ? atoi(env) : 2;
+        n_slots = std::max(1, std::min(n_slots, (int)rb200_ctx::kMaxSlots));
+        if (c->stage_timing) n_slots = 1;                      // per-stage events need the chunks serialised
+        n_slots = std::min(n_slots, (n_cpi + G - 1) / G);
+        for (int i = 0; i < n_slots; ++i) {
+            rb200_ctx::Slot& sl = c->slots[i];
+            CK(c, sl.pc.ensure((size_t)G * cpi_cells * sizeof(float2)));
+            CK(c, sl.colmask.ensure((size_t)G * C * R * sizeof(unsigned long long)));
+            CK(c, sl.vlist.ensure((size_t)k.max_det * sizeof(rb200_det)));
+        }
+    } else {
+        CK(c, c->pc.ensure((size_t)G * cpi_cells * sizeof(float2)));
+        CK(c, c->vmask.ensure((size_t)G * C * P * Rw * sizeof(uint32_t)));
+    }
+    CK(c, cudaEventRecord(c->ev0, st));
+    if (n_slots > 1) {
+        CK(c, cudaEventRecord(c->fork_ev, st));
+        for (int i = 0; i < n_slots; ++i) CK(c, cudaStreamWaitEvent(c->slots[i].stream, c->fork_ev, 0));
     }
     int chunk_idx = 0;
-    CK(c, cudaEventRecord(c->ev0, st));
-    for (int c0 = 0; c0 < n_cpi; c0 += G) {
+    for (int c0 = 0; c0 < n_cpi; c0 += G, ++chunk_idx) {
         const int g = std::min(G, n_cpi - c0);
         const int16_t* raw_chunk = raw_dev + (size_t)c0 * cpi_cells * 2;
         float* rdm_chunk = rdm_dev ? rdm_base + (size_t)c0 * cpi_cells : rdm_base;
+        rb200_ctx::Slot& sl = c->slots[chunk_idx % n_slots];
+        cudaStream_t cs = (fused && n_slots > 1) ? sl.stream : st;
+        float2* pc_buf = fused ? sl.pc.as<float2>() : c->pc.as<float2>();
         const bool timed = c->stage_timing && c->stage_used + 4 <= 65536;
-        if (timed) { stage_event(c, st); c->stage_cpis.push_back(g); }
-        int rc = run_pc(c, c->plan, true, raw_chunk, c->pc.as<float2>(), R, R, C, P, g * P, 0,
-                        c->gain_n ? c->gain.as<float>() : nullptr, st);
+        if (timed) { stage_event(c, cs); c->stage_cpis.push_back(g); }
+        int rc = run_pc(c, c->plan, true, raw_chunk, pc_buf, R, R, C, P, g * P, 0, c->gain_n ? c->gain.as<float>() : nullptr, cs);
         if (rc) return rc;
-        if (timed) stage_event(c, st);
+        if (timed) stage_event(c, cs);
         cp.cpi0 = c0;
         if (fused) {
             // K2 + velocity CFAR in one kernel (register-resident Doppler columns), then the sparse range stage
-            m64.in = c->pc.as<float2>();
+            m64.in = pc_buf;
             m64.out = rdm_chunk;
             m64.cpi0 = c0;
-            CK(c, launch_mtd64(m64, g * C, true, st));
+            m64.dets = sl.vlist.p;
+            m64.det_count = sl.count.as<int>();
+            m64.colmask = sl.colmask.as<unsigned long long>();
+            CK(c, launch_mtd64(m64, g * C, true, cs));
             c->launches++;
-            if (timed) stage_event(c, st);
-            if (cp.range_stage) {
-                CK(c, launch_cfar_r64(rdm_chunk, cp, (float)k.cfar_t_r, c->dets_v.p, c->counters.as<int>(), c->dets_2d.p,
-                                      c->colmask.as<unsigned long long>(), R, chunk_idx & 1, c->errflag.as<int>(), c->n_sms, st));
-                c->launches++;
-            }
+            if (timed) stage_event(c, cs);
+            CK(c, launch_cfar_r64(rdm_chunk, cp, (float)k.cfar_t_r, sl.vlist.p, sl.count.as<int>(), c->dets_v.p, c->dets_2d.p,
+                                  c->counters.as<int>(), sl.colmask.as<unsigned long long>(), R, c->errflag.as<int>(), c->n_sms, cs));
+            c->launches++;
         } else {
-            rc = run_mtd(c, c->pc.as<float2>(), rdm_chunk, P, R, R, R, g * C, k.kaiser_beta, k.zero_v_div, k.mti_lag, st);
+            rc = run_mtd(c, pc_buf, rdm_chunk, P, R, R, R, g * C, k.kaiser_beta, k.zero_v_div, k.mti_lag, cs);
             if (rc) return rc;
-            if (timed) stage_event(c, st);
+            if (timed) stage_event(c, cs);
             if (cp.v_hi > cp.v_lo) {
                 // hits of this chunk start where the list currently ends
-                CK(c, cudaMemcpyAsync(c->counters.as<int>() + 2, c->counters.as<int>() + 0, sizeof(int), cudaMemcpyDeviceToDevice, st));
+                CK(c, cudaMemcpyAsync(c->counters.as<int>() + 2, c->counters.as<int>() + 0, sizeof(int), cudaMemcpyDeviceToDevice, cs));
                 CK(c, launch_cfar_f32(rdm_chunk, cp, (float)k.cfar_t_r, (float)k.cfar_t_v, g * C, c->dets_v.p, c->counters.as<int>() + 0,
                                       c->dets_2d.p, c->counters.as<int>() + 1, c->vmask.as<uint32_t>(), nullptr, nullptr,
-                                      c->errflag.as<int>(), st));
+                                      c->errflag.as<int>(), cs));
                 c->launches += cp.range_stage ? 2 : 1;
             }
         }
-        ++chunk_idx;
-        if (timed) stage_event(c, st);
+        if (timed) stage_event(c, cs);
         c->last_chunk_cpis = g;
+        c->last_pc = pc_buf;
+    }
+    if (n_slots > 1) {
+        for (int i = 0; i < n_slots; ++i) {
+            CK(c, cudaEventRecord(c->slots[i].done, c->slots[i].stream));
+            CK(c, cudaStreamWaitEvent(st, c->slots[i].done, 0));
+        }
     }
     CK(c, cudaEventRecord(c->ev1, st));
     c->have_timing = true;
@@ -1077,7 +1125,9 @@ extern "C" int rb200_debug_fetch_pc(rb200_ctx* c, int cpi_in_chunk, float* out_r
     if (!c || !out_ri || cpi_in_chunk < 0 || cpi_in_chunk >= c->last_chunk_cpis) return fail(c, RB200_ERR_ARG, "debug_fetch_pc: bad argument");
     cudaSetDevice(c->device);
     const size_t cpi_cells = (size_t)c->cfg.n_prt * c->cfg.n_range * c->cfg.n_lanes;
-    CK(c, cudaMemcpy(out_ri, c->pc.as<float2>() + (size_t)cpi_in_chunk * cpi_cells, cpi_cells * sizeof(float2), cudaMemcpyDeviceToHost));
+    if (!c->last_pc) return fail(c, RB200_ERR_ARG, "debug_fetch_pc: no chain call yet");
+    CK(c, cudaDeviceSynchronize());
+    CK(c, cudaMemcpy(out_ri, c->last_pc + (size_t)cpi_in_chunk * cpi_cells, cpi_cells * sizeof(float2), cudaMemcpyDeviceToHost));
     return RB200_OK;
 }
 

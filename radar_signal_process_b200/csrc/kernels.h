@@ -23,8 +23,9 @@ int mtd_generic_max_p();
 // ---- K2 for P = 64 fused with the velocity CFAR stage, and its sparse range stage (mtd64_kernel.cu)
 bool mtd64_fused_supported(int P, int ref_v, int guard_v, int n0, int mti_lag);
 cudaError_t launch_mtd64(const Mtd64Params& p, int n_slabs, bool with_cfar, cudaStream_t st);
-cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, const void* dets_v, int* counters, void* dets_2d,
-                            const unsigned long long* colmask, int cols_ld, int chunk_parity, int* err_flag, int n_sms, cudaStream_t st);
+cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, const void* slot_v, int* slot_count, void* dets_v,
+                            void* dets_2d, int* gcount, const unsigned long long* colmask, int cols_ld, int* err_flag, int n_blocks,
+                            cudaStream_t st);
 
 // ---- K3 CFAR (cfar_kernels.cu)
 // chain variant: float RDM [slab][V][R] row-major -> velocity-hit list + 2-D list (+ optional dense uint8 flags)

@@ -140,13 +140,6 @@ mtd64_kernel(const Mtd64Params p) {
     }
 }
 
-// Range stage for the fused path: one (grid-stride) thread per velocity hit; same election rule as
-// cfar_r_kernel but the velocity-hit membership test reads the per-column 64-bit masks.
-__global__ void cfar_r64_kernel(const float* __restrict__ rdm, const CfarParams p, float t_r,
-                                const rb200_det* __restrict__ dets_v, int* __restrict__ counters,
-                                rb200_det* __restrict__ dets_2d, const unsigned long long* __restrict__ colmask,
-                                int cols_ld, int chunk_parity, int* err_flag);
-
 __device__ __forceinline__ bool cfar_decide_f32(const float* __restrict__ row, int y, int N, int ref, int guard, float thr, int method, int* err_flag) {
     const int l1 = y - guard - ref;
     const int r1 = y + guard + 1;
@@ -180,17 +173,24 @@ __device__ __forceinline__ int cfar_elect_f32(const float* __restrict__ row, int
     return best;
 }
 
+// Range stage for the fused path (CW/executeCFAR.m:45-75): one (grid-stride) thread per velocity hit of
+// this chunk; elects the first maximum among the passing cells of {r-1,r,r+1}, de-duplicates through the
+// per-column velocity-hit masks, appends the 2-D record to the global list and moves the velocity record
+// from the per-slot scratch list to the global one.  The last block to finish re-arms the slot counters.
 __global__ void cfar_r64_kernel(const float* __restrict__ rdm, const CfarParams p, float t_r,
-                                const rb200_det* __restrict__ dets_v, int* __restrict__ counters,
-                                rb200_det* __restrict__ dets_2d, const unsigned long long* __restrict__ colmask,
-                                int cols_ld, int chunk_parity, int* err_flag) {
-    // counters: [0] velocity hits so far, [1] 2-D records so far, [2 + parity] first hit of this chunk.
-    const int start = counters[2 + chunk_parity];
-    int n = counters[0];
-    if (blockIdx.x == 0 && threadIdx.x == 0) counters[2 + (chunk_parity ^ 1)] = n;   // next chunk starts here
+                                const rb200_det* __restrict__ slot_v, int* __restrict__ slot_count,
+                                rb200_det* __restrict__ dets_v, rb200_det* __restrict__ dets_2d, int* __restrict__ gcount,
+                                const unsigned long long* __restrict__ colmask, int cols_ld, int* err_flag) {
+    int n = slot_count[0];
+    const int true_n = n;
     if (n > p.max_det) n = p.max_det;
-    for (int i = start + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const rb200_det h = dets_v[i];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const rb200_det h = slot_v[i];
+        {
+            const int slot = atomicAdd(&gcount[0], 1);
+            if (slot < p.max_det) dets_v[slot] = h;
+        }
+        if (!p.range_stage) continue;
         const int slab = (int)(h.cpi - p.cpi0) * p.n_lanes + h.lane;
         const int v = h.v, r = (int)h.r;
         const float* row = rdm + ((size_t)slab * p.V + v) * p.R;
@@ -204,7 +204,7 @@ __global__ void cfar_r64_kernel(const float* __restrict__ rdm, const CfarParams 
             if (cfar_elect_f32(row, rr, p, t_r, nullptr) == c) owner = false;
         }
         if (!owner) continue;
-        const int slot = atomicAdd(&counters[1], 1);
+        const int slot = atomicAdd(&gcount[1], 1);
         if (slot < p.max_det) {
             rb200_det d;
             d.cpi = h.cpi;
@@ -214,6 +214,17 @@ __global__ void cfar_r64_kernel(const float* __restrict__ rdm, const CfarParams 
             d.kind = RB200_DET_2D;
             d.amp = row[c];
             dets_2d[slot] = d;
+        }
+    }
+    // hits dropped by the per-slot capacity still count (the host reports RB200_ERR_OVERFLOW)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && true_n > n) atomicAdd(&gcount[0], true_n - n);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(&slot_count[1], 1);
+        if (ticket == (int)gridDim.x - 1) {      // last block: re-arm the slot for its next chunk
+            slot_count[0] = 0;
+            slot_count[1] = 0;
         }
     }
 }
@@ -232,10 +243,11 @@ cudaError_t launch_mtd64(const Mtd64Params& p, int n_slabs, bool with_cfar, cuda
     return cudaGetLastError();
 }
 
-cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, const void* dets_v, int* counters, void* dets_2d,
-                            const unsigned long long* colmask, int cols_ld, int chunk_parity, int* err_flag, int n_sms, cudaStream_t st) {
-    cfar_r64_kernel<<<n_sms * 2, 128, 0, st>>>(rdm, p, t_r, (const rb200_det*)dets_v, counters, (rb200_det*)dets_2d, colmask, cols_ld,
-                                               chunk_parity, err_flag);
+cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, const void* slot_v, int* slot_count, void* dets_v,
+                            void* dets_2d, int* gcount, const unsigned long long* colmask, int cols_ld, int* err_flag, int n_blocks,
+                            cudaStream_t st) {
+    cfar_r64_kernel<<<n_blocks, 128, 0, st>>>(rdm, p, t_r, (const rb200_det*)slot_v, slot_count, (rb200_det*)dets_v,
+                                              (rb200_det*)dets_2d, gcount, colmask, cols_ld, err_flag);
     return cudaGetLastError();
 }
 
