@@ -9,7 +9,27 @@ CU_SRCS   := $(CSRC)/api.cu $(CSRC)/pc_kernels.cu $(CSRC)/mtd_kernels.cu $(CSRC)
 CU_OBJS   := $(CU_SRCS:.cu=.o)
 HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/radar_b200.h
 
-all: $(LIB)
+MEXDIR    := mex
+MEXBUILD  := mex/build
+MEX_NAMES := fun_MTD_produce fun_lss_pulse_compression fun_pulse_compression fun_Process_MTD fun_0v_pressing executeCFAR Function_CFAR1D_sub Function_CFAR1D_sub_fixCells
+MEX_SOS   := $(addprefix $(MEXBUILD)/,$(addsuffix .so,$(MEX_NAMES))) $(MEXBUILD)/fun_0v_pressing_cw.so
+SHIM      := $(MEXBUILD)/librbmexshim.so
+MEXFLAGS  := -O2 -fPIC -shared -Wall -I$(MEXDIR)/shim -I$(MEXDIR) -Wno-unused-function
+
+all: $(LIB) mex-shim
+
+# MEX gateways compiled against the shim mex.h and linked to the C-ABI library (tests run them without MATLAB/Octave)
+mex-shim: $(SHIM) $(MEX_SOS)
+
+$(SHIM): $(MEXDIR)/shim/mex_shim.c $(MEXDIR)/shim/mex.h
+	@mkdir -p $(MEXBUILD)
+	gcc -O2 -fPIC -shared -Wall -I$(MEXDIR)/shim -o $@ $<
+
+$(MEXBUILD)/%.so: $(MEXDIR)/%.cpp $(MEXDIR)/rb200_mex_common.h $(MEXDIR)/rb200_waveform_literals.h include/radar_b200.h $(LIB) $(SHIM)
+	$(CXX) $(MEXFLAGS) -o $@ $< -L$(PKG) -lradar_b200 -L$(MEXBUILD) -lrbmexshim -Wl,-rpath,'$$ORIGIN/../../$(PKG)' -Wl,-rpath,'$$ORIGIN'
+
+$(MEXBUILD)/fun_0v_pressing_cw.so: $(MEXDIR)/fun_0v_pressing.cpp $(MEXDIR)/rb200_mex_common.h include/radar_b200.h $(LIB) $(SHIM)
+	$(CXX) $(MEXFLAGS) -DRB200_ZERO_V_DIV=20 -o $@ $< -L$(PKG) -lradar_b200 -L$(MEXBUILD) -lrbmexshim -Wl,-rpath,'$$ORIGIN/../../$(PKG)' -Wl,-rpath,'$$ORIGIN'
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) $(EXTRA_NVFLAGS) -c $< -o $@
@@ -19,5 +39,6 @@ $(LIB): $(CU_OBJS)
 
 clean:
 	rm -f $(CU_OBJS) $(LIB)
+	rm -rf $(MEXBUILD)
 
-.PHONY: all clean
+.PHONY: all clean mex-shim

@@ -1,0 +1,101 @@
+"""The MEX gateways executed on the GPU through the shim runtime, against the CPU oracle: this is the
+reference-facing boundary a MATLAB/Octave session would hit (same names, argument order, 1-based indices,
+column-major doubles)."""
+import numpy as np
+import pytest
+
+from mexharness import Mex, MexError
+from oracle import mcode, synth, vec
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, tol=1e-4):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.max(np.abs(a - b)) <= tol * np.max(np.abs(b))
+
+
+def _rc(rng, *s):
+    return rng.normal(size=s) + 1j * rng.normal(size=s)
+
+
+def test_mex_fun_pulse_compression():
+    rng = np.random.default_rng(1)
+    s0, x = _rc(rng, 67), _rc(rng, 300)
+    got = Mex("fun_pulse_compression")(s0, x)
+    assert got.shape == (1, 366)
+    _close(got[0], mcode.fun_pulse_compression(s0, x))
+    got = Mex("fun_pulse_compression")(s0.real, x.real)           # real inputs: imag treated as 0
+    _close(got[0], mcode.fun_pulse_compression(s0.real, x.real))
+
+
+def test_mex_fun_lss_pulse_compression_both_generations():
+    rng = np.random.default_rng(2)
+    p2, p3 = mcode.load_pulse_literals()
+    echo = np.rint(100 * _rc(rng, 5, 1031))
+    got = Mex("fun_lss_pulse_compression")(echo, 0, mcode.pulse1_mp(), p2, p3)
+    _close(got, mcode.fun_lss_pulse_compression_mp(echo, None, p2, p3))
+    with pytest.raises(MexError) as e:
+        Mex("fun_lss_pulse_compression")(echo, 0, 1.0, p2[:70], p3)
+    assert e.value.ident == "radar_b200:pc:dimensionMismatch"
+    params = dict(fs=25e6, B=20e6, tao=[0.16e-6, 8e-6, 28e-6], point_prt=[3404, 228, 723, 2453])
+    pulse1, pulse2, pulse3 = mcode.ideal_pulses_mtd(params)
+    echo = np.rint(100 * _rc(rng, 3, 3404))
+    got = Mex("fun_lss_pulse_compression")(echo, params, 0, pulse1, pulse2, pulse3, 228, 723, 2453)
+    _close(got, mcode.fun_lss_pulse_compression_mtd(echo, pulse1, pulse2, pulse3, 228, 723, 2453))
+    with pytest.raises(MexError) as e:
+        Mex("fun_lss_pulse_compression")(echo, params, 0, pulse1, pulse2, pulse3, 228, 723, 2454)
+    assert e.value.ident == "radar_b200:pc:indexOutOfRange"
+
+
+def test_mex_fun_Process_MTD_and_0v():
+    rng = np.random.default_rng(3)
+    x = 100 * _rc(rng, 64, 21)
+    got = Mex("fun_Process_MTD")(x, 21, 64)
+    want = mcode.fun_Process_MTD(x, 21, 64)
+    _close(got, want)
+    with pytest.raises(MexError) as e:
+        Mex("fun_Process_MTD")(x, 22, 64)
+    assert e.value.ident == "radar_b200:mtd:indexOutOfRange"
+    with pytest.raises(MexError) as e:
+        Mex("fun_Process_MTD")(x, 21, 63)
+    assert e.value.ident == "radar_b200:mtd:dimensionMismatch"
+    assert np.array_equal(Mex("fun_0v_pressing")(want), mcode.fun_0v_pressing(want, 150))
+    m155 = rng.rayleigh(1, size=(155, 7))
+    assert np.array_equal(Mex("fun_0v_pressing_cw")(m155), mcode.fun_0v_pressing(m155, 20))
+
+
+def test_mex_fun_MTD_produce_1arg_and_2arg():
+    echo = synth.s2_frame()
+    got = Mex("fun_MTD_produce")(echo)
+    _close(got, mcode.fun_MTD_produce_mp(echo))
+    rng = np.random.default_rng(4)
+    params = dict(prt=1e-4, prf=1e4, prtNum=16, fs=25e6, deltaR=6.0, fc=9.4e9, wavelength=0.0319, B=20e6,
+                  tao=[0.16e-6, 8e-6, 28e-6], point_prt=[3404, 228, 723, 2453], debug=dict(show_PC=0, show_FFT=0, graph=0))
+    echo = np.rint(100 * _rc(rng, 16, 3404))
+    got = Mex("fun_MTD_produce")(echo, params)
+    _close(got, mcode.fun_MTD_produce_mtd(echo, params))
+    bad = dict(params, point_prt=[3404, 228, 723, 2500])
+    with pytest.raises(MexError) as e:
+        Mex("fun_MTD_produce")(echo, bad)
+    assert e.value.ident == "radar_b200:pc:indexOutOfRange"
+
+
+def test_mex_executeCFAR_and_cfar1d_bit_identical():
+    rng = np.random.default_rng(5)
+    x = rng.rayleigh(1.0, size=(64, 200))
+    for _ in range(8):
+        x[rng.integers(0, 64), rng.integers(0, 200)] = 30.0
+    args = (5, 7, 3.0, 0, 5, 7, 3.0, 0, 1, 1)
+    f, fv = Mex("executeCFAR")(x, *args, nargout=2)
+    fo, fvo = mcode.executeCFAR(x, *args)
+    assert np.array_equal(f, fo) and np.array_equal(fv, fvo)
+    f1 = Mex("executeCFAR")(x, *args)                                 # single output
+    assert np.array_equal(f1, fo)
+    with pytest.raises(MexError) as e:
+        Mex("executeCFAR")(x[:20], *args)
+    assert e.value.ident == "radar_b200:cfar:indexOutOfRange"
+    d = rng.rayleigh(1.0, size=(6, 60))
+    assert np.array_equal(Mex("Function_CFAR1D_sub")(d, 5, 7, 1.5, 1), mcode.Function_CFAR1D_sub(d, 5, 7, 1.5, 1))
+    assert np.array_equal(Mex("Function_CFAR1D_sub_fixCells")(d, 5, 7, 1.5, 0, [1, 4], [2, 30, 59]),
+                          mcode.Function_CFAR1D_sub_fixCells(d, 5, 7, 1.5, 0, [1, 4], [2, 30, 59]))

@@ -36,7 +36,7 @@ def main():
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")
-    stall_cols = [i for i, h in enumerate(hdr) if "warp_issue_stalled" in h and h.endswith("per_warp_active.pct") and "not_issued" not in h]
+    stall_cols = [i for i, h in enumerate(hdr) if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
     for r in rows[2:2 + limit]:
         print("== %s" % r[ki][:90])
         for name, key in WANT:
@@ -46,11 +46,11 @@ def main():
         st = []
         for i in stall_cols:
             try:
-                st.append((float(r[i].replace(",", "")), hdr[i].replace("smsp__warp_issue_stalled_", "").replace("_per_warp_active.pct", "")))
+                st.append((float(r[i].replace(",", "")), hdr[i].replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
             except ValueError:
                 pass
         st.sort(reverse=True)
-        print("   stalls(%% of warp-active): " + ", ".join("%s %.0f" % (n, v) for v, n in st[:6]))
+        print("   stalled warps per issue-active cycle: " + ", ".join("%s %.2f" % (n, v) for v, n in st[:7]))
 
 
 if __name__ == "__main__":
