@@ -155,7 +155,7 @@ struct rb200_ctx {
     struct Slot {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
-        DevBuf pc, colmask, vlist, count;
+        DevBuf pc, colmask, vlist, count, raw, rdm;
     };
     static const int kMaxSlots = 4;
     Slot slots[kMaxSlots];
@@ -572,7 +572,7 @@ extern "C" int rb200_destroy(rb200_ctx* c) {
     for (int i = 0; i < rb200_ctx::kMaxSlots; ++i) {
         rb200_ctx::Slot& sl = c->slots[i];
         if (sl.stream) cudaStreamSynchronize(sl.stream);
-        sl.pc.release(); sl.colmask.release(); sl.vlist.release(); sl.count.release();
+        sl.pc.release(); sl.colmask.release(); sl.vlist.release(); sl.count.release(); sl.raw.release(); sl.rdm.release();
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
@@ -929,14 +929,17 @@ static int chunk_size(const rb200_ctx* c) {
     const char* env = getenv("RB200_CHUNK");
     int g = env ? atoi(env) : c->cfg.chunk_cpi;
     if (g <= 0) {
-        // default: keep raw + PC + RDM of one chunk inside ~96 MB of the 126 MB L2
+        // default: a few tens of MB of PC intermediate per chunk (S3: 4 CPIs); measured flat between 2 and 8
         const double per_cpi = (double)c->cfg.n_prt * c->cfg.n_range * c->cfg.n_lanes * 16.0;
-        g = (int)std::floor(96e6 / per_cpi);
+        g = (int)std::floor(280e6 / per_cpi);
     }
     return std::max(1, std::min(g, c->cfg.max_cpi));
 }
 
-static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float* rdm_dev, cudaStream_t st) {
+// raw_host / rdm_host (optional): host buffers staged chunk by chunk on the chunk's own stream, so the H2D copy
+// of chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i (three slots, two copy engines).
+static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float* rdm_dev, cudaStream_t st,
+                         const int16_t* raw_host = nullptr, float* rdm_host = nullptr) {
     const rb200_config& k = c->cfg;
     const int P = k.n_prt, R = k.n_range, C = k.n_lanes;
     if (n_cpi < 1 || n_cpi > k.max_cpi) return fail(c, RB200_ERR_ARG, "chain: n_cpi must be in 1..max_cpi");
@@ -947,7 +950,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     CK(c, c->dets_v.ensure((size_t)k.max_det * sizeof(rb200_det)));
     CK(c, c->dets_2d.ensure((size_t)k.max_det * sizeof(rb200_det)));
     float* rdm_base = rdm_dev;
-    if (!rdm_base) {
+    if (!rdm_base && !rdm_host) {
         CK(c, c->rdm.ensure((size_t)G * cpi_cells * sizeof(float)));
         rdm_base = c->rdm.as<float>();
     }
@@ -984,7 +987,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         m64.max_det = k.max_det;
         m64.n_lanes = C;
         const char* env = getenv("RB200_SLOTS");
-        n_slots = env ? atoi(env) : 2;
+        n_slots = env ? atoi(env) : 3;
         n_slots = std::max(1, std::min(n_slots, (int)rb200_ctx::kMaxSlots));
         if (c->stage_timing) n_slots = 1;                      // per-stage events need the chunks serialised
         n_slots = std::min(n_slots, (n_cpi + G - 1) / G);
@@ -998,6 +1001,10 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         CK(c, c->pc.ensure((size_t)G * cpi_cells * sizeof(float2)));
         CK(c, c->vmask.ensure((size_t)G * C * P * Rw * sizeof(uint32_t)));
     }
+    for (int i = 0; i < n_slots; ++i) {
+        if (raw_host) CK(c, c->slots[i].raw.ensure((size_t)G * cpi_cells * 4));
+        if (rdm_host) CK(c, c->slots[i].rdm.ensure((size_t)G * cpi_cells * sizeof(float)));
+    }
     CK(c, cudaEventRecord(c->ev0, st));
     if (n_slots > 1) {
         CK(c, cudaEventRecord(c->fork_ev, st));
@@ -1006,10 +1013,14 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     int chunk_idx = 0;
     for (int c0 = 0; c0 < n_cpi; c0 += G, ++chunk_idx) {
         const int g = std::min(G, n_cpi - c0);
-        const int16_t* raw_chunk = raw_dev + (size_t)c0 * cpi_cells * 2;
-        float* rdm_chunk = rdm_dev ? rdm_base + (size_t)c0 * cpi_cells : rdm_base;
         rb200_ctx::Slot& sl = c->slots[chunk_idx % n_slots];
         cudaStream_t cs = (fused && n_slots > 1) ? sl.stream : st;
+        const int16_t* raw_chunk = raw_dev ? raw_dev + (size_t)c0 * cpi_cells * 2 : nullptr;
+        if (raw_host) {
+            CK(c, cudaMemcpyAsync(sl.raw.p, raw_host + (size_t)c0 * cpi_cells * 2, (size_t)g * cpi_cells * 4, cudaMemcpyHostToDevice, cs));
+            raw_chunk = sl.raw.as<int16_t>();
+        }
+        float* rdm_chunk = rdm_host ? sl.rdm.as<float>() : (rdm_dev ? rdm_base + (size_t)c0 * cpi_cells : rdm_base);
         float2* pc_buf = fused ? sl.pc.as<float2>() : c->pc.as<float2>();
         const bool timed = c->stage_timing && c->stage_used + 4 <= 65536;
         if (timed) { stage_event(c, cs); c->stage_cpis.push_back(g); }
@@ -1044,6 +1055,8 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
                 c->launches += cp.range_stage ? 2 : 1;
             }
         }
+        if (rdm_host)
+            CK(c, cudaMemcpyAsync(rdm_host + (size_t)c0 * cpi_cells, rdm_chunk, (size_t)g * cpi_cells * sizeof(float), cudaMemcpyDeviceToHost, cs));
         if (timed) stage_event(c, cs);
         c->last_chunk_cpis = g;
         c->last_pc = pc_buf;
@@ -1098,26 +1111,11 @@ extern "C" int rb200_chain_i16(rb200_ctx* c, const int16_t* raw, int n_cpi, floa
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     const rb200_config& k = c->cfg;
     if (n_cpi < 1 || n_cpi > k.max_cpi) return fail(c, RB200_ERR_ARG, "chain: n_cpi must be in 1..max_cpi");
-    const size_t cpi_cells = (size_t)k.n_prt * k.n_range * k.n_lanes;
-    const int16_t* raw_dev = raw;
-    if (!is_device_ptr(raw)) {
-        CK(c, c->raw.ensure((size_t)n_cpi * cpi_cells * 4));
-        CK(c, cudaMemcpyAsync(c->raw.p, raw, (size_t)n_cpi * cpi_cells * 4, cudaMemcpyHostToDevice, st));
-        raw_dev = c->raw.as<int16_t>();
-    }
-    float* rdm_dev = nullptr;
-    bool rdm_to_host = false;
-    if (rdm_out) {
-        if (is_device_ptr(rdm_out)) rdm_dev = rdm_out;
-        else {
-            CK(c, c->rdm.ensure((size_t)std::max(n_cpi, chunk_size(c)) * cpi_cells * sizeof(float)));
-            rdm_dev = c->rdm.as<float>();
-            rdm_to_host = true;
-        }
-    }
-    int rc = chain_enqueue(c, raw_dev, n_cpi, rdm_dev, st);
+    const bool raw_on_dev = is_device_ptr(raw);
+    const bool rdm_on_dev = rdm_out && is_device_ptr(rdm_out);
+    int rc = chain_enqueue(c, raw_on_dev ? raw : nullptr, n_cpi, rdm_on_dev ? rdm_out : nullptr, st,
+                           raw_on_dev ? nullptr : raw, (rdm_out && !rdm_on_dev) ? rdm_out : nullptr);
     if (rc) return rc;
-    if (rdm_to_host) CK(c, cudaMemcpyAsync(rdm_out, rdm_dev, (size_t)n_cpi * cpi_cells * sizeof(float), cudaMemcpyDeviceToHost, st));
     return chain_fetch(c, dets, dets && is_device_ptr(dets), n_det, st);
 }
 
