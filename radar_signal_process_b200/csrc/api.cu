@@ -379,7 +379,8 @@ static int run_pc(rb200_ctx* ctx, const Plan& plan, bool wire, const void* in, f
         const int lt = pc_tile_lanes(c.nt, wire);
         const int n_groups = wire ? n_groups_wire : (n_lines + lt - 1) / lt;
         if (n_groups <= 0) continue;
-        CK(ctx, launch_pc_fft(c.nt, wire, p, c.n_tiles, n_groups, st));
+        if (wire && C == 16 && c.nt == 256 && !getenv("RB200_NO_TMA")) CK(ctx, launch_pc_fft_tma(p, c.n_tiles, n_groups, ctx->n_sms, st));
+        else CK(ctx, launch_pc_fft(c.nt, wire, p, c.n_tiles, n_groups, st));
         ctx->launches++;
     }
     for (size_t i = 0; i < plan.segs.size(); ++i) {
@@ -1036,7 +1037,8 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
             m64.dets = sl.vlist.p;
             m64.det_count = sl.count.as<int>();
             m64.colmask = sl.colmask.as<unsigned long long>();
-            CK(c, launch_mtd64(m64, g * C, true, cs));
+            if ((R % 2) == 0 && !getenv("RB200_NO_TMA_MTD")) CK(c, launch_mtd64_tma(m64, g * C, c->n_sms, cs));
+            else CK(c, launch_mtd64(m64, g * C, true, cs));
             c->launches++;
             if (timed) stage_event(c, cs);
             CK(c, launch_cfar_r64(rdm_chunk, cp, (float)k.cfar_t_r, sl.vlist.p, sl.count.as<int>(), c->dets_v.p, c->dets_2d.p,

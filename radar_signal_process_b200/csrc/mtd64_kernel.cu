@@ -22,6 +22,7 @@
 #include "tw64.cuh"
 #include "kernels.h"
 #include "../../include/radar_b200.h"
+#include <algorithm>
 
 namespace rb {
 
@@ -31,22 +32,14 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     return r;
 }
 
-template <int REF, int GUARD, int N0, bool CFAR>
-__global__ void __launch_bounds__(128)
-mtd64_kernel(const Mtd64Params p) {
-    constexpr int P = 64;
-    const int slab = blockIdx.y;
-    const int r = blockIdx.x * 128 + threadIdx.x;
-    const bool ok = r < p.cols;
-    const int rc = ok ? r : p.cols - 1;      // clamp: inactive threads still take part in warp votes
-    const float2* col = p.in + (size_t)slab * P * p.in_ld + rc;
+#ifndef RB200_MTD64_MINB
+#define RB200_MTD64_MINB 3
+#endif
 
-    float2 v[P];
-#pragma unroll
-    for (int prt = 0; prt < P; ++prt) {
-        const float2 x = __ldg(col + (size_t)prt * p.in_ld);
-        v[prt] = make_float2(x.x * p.win[prt], x.y * p.win[prt]);
-    }
+// The column work shared by both kernel variants: v[] holds the 64 windowed slow-time samples of range cell r.
+template <int REF, int GUARD, int N0, bool CFAR>
+__device__ __forceinline__ void mtd64_column(float2 (&v)[64], const Mtd64Params& p, int slab, int r, bool ok) {
+    constexpr int P = 64;
     // ---- 64-point DIF: step 1, radix-8 over j for every q (elements q + 8j), twiddle w64^(q*k0) ----
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -91,8 +84,6 @@ mtd64_kernel(const Mtd64Params p) {
     unsigned long long hits = 0ull;
 #pragma unroll
     for (int y = 0; y < NV; ++y) {
-        constexpr int dummy = 0;
-        (void)dummy;
         const int l1 = y - GUARD - REF;
         const int r2 = y + GUARD + REF;
         const bool okL = l1 >= 0;
@@ -137,6 +128,97 @@ mtd64_kernel(const Mtd64Params p) {
             reinterpret_cast<rb200_det*>(p.dets)[slot] = d;
         }
         ++slot;
+    }
+}
+
+template <int REF, int GUARD, int N0, bool CFAR>
+__global__ void __launch_bounds__(128, RB200_MTD64_MINB)
+mtd64_kernel(const Mtd64Params p) {
+    constexpr int P = 64;
+    const int slab = blockIdx.y;
+    const int r = blockIdx.x * 128 + threadIdx.x;
+    const bool ok = r < p.cols;
+    const int rc = ok ? r : p.cols - 1;      // clamp: inactive threads still take part in warp votes
+    const float2* col = p.in + (size_t)slab * P * p.in_ld + rc;
+    float2 v[P];
+    // loads in the order the first butterflies consume them (q-major: rows q, q+8, ..., q+56)
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int prt = q + 8 * j;
+            const float2 x = __ldg(col + (size_t)prt * p.in_ld);
+            v[prt] = make_float2(x.x * p.win[prt], x.y * p.win[prt]);
+        }
+    mtd64_column<REF, GUARD, N0, CFAR>(v, p, slab, r, ok);
+}
+
+// Persistent variant: the 64 x 128 tile of the next work item is fetched by 64 TMA bulk copies (one 1 KB row
+// each, one mbarrier) into shared memory while the CTA transforms the current item out of registers, so the
+// HBM/L2 read stream overlaps the butterflies.  Needs 16-byte aligned rows (even in_ld and cols).
+__device__ __forceinline__ uint32_t m64_smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+
+template <int REF, int GUARD, int N0, bool CFAR>
+__global__ void __launch_bounds__(128, RB200_MTD64_MINB)
+mtd64_tma_kernel(const Mtd64Params p, int tiles_per_slab, int n_items) {
+    constexpr int P = 64;
+    extern __shared__ __align__(128) float2 tile[];    // [64][128]
+    __shared__ __align__(8) uint64_t mbar;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(m64_smem_u32(&mbar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto expect = [&](int item) {          // thread 0
+        const int c0 = (item % tiles_per_slab) * 128;
+        const uint32_t bytes = (uint32_t)min(128, p.cols - c0) * 8u * P;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m64_smem_u32(&mbar)), "r"(bytes) : "memory");
+    };
+    auto copy_row = [&](int item) {        // threads 0..63: one PRT row each
+        const int slab = item / tiles_per_slab;
+        const int c0 = (item - slab * tiles_per_slab) * 128;
+        const uint32_t bytes = (uint32_t)min(128, p.cols - c0) * 8u;
+        const float2* src = p.in + ((size_t)slab * P + t) * p.in_ld + c0;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(m64_smem_u32(tile + t * 128)),
+                     "l"(src), "r"(bytes), "r"(m64_smem_u32(&mbar))
+                     : "memory");
+    };
+    int item = blockIdx.x;
+    if (item < n_items) {
+        if (t == 0) expect(item);
+        __syncthreads();
+        if (t < P) copy_row(item);
+    }
+    for (int it = 0; item < n_items; item += gridDim.x, ++it) {
+        const int slab = item / tiles_per_slab;
+        const int r = (item - slab * tiles_per_slab) * 128 + t;
+        const bool ok = r < p.cols;
+        {
+            const uint32_t parity = (uint32_t)(it & 1);
+            asm volatile(
+                "{\n"
+                ".reg .pred P1;\n"
+                "LAB_WAIT:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                "@P1 bra DONE;\n"
+                "bra LAB_WAIT;\n"
+                "DONE:\n"
+                "}" ::"r"(m64_smem_u32(&mbar)),
+                "r"(parity)
+                : "memory");
+        }
+        float2 v[P];
+#pragma unroll
+        for (int prt = 0; prt < P; ++prt) {
+            const float2 x = tile[prt * 128 + t];
+            v[prt] = make_float2(x.x * p.win[prt], x.y * p.win[prt]);
+        }
+        const int next = item + gridDim.x;
+        if (t == 0 && next < n_items) expect(next);
+        __syncthreads();                    // every thread has its column in registers: the tile buffer is free
+        if (next < n_items && t < P) copy_row(next);
+        mtd64_column<REF, GUARD, N0, CFAR>(v, p, slab, r, ok);
     }
 }
 
@@ -240,6 +322,23 @@ cudaError_t launch_mtd64(const Mtd64Params& p, int n_slabs, bool with_cfar, cuda
     if (n_slabs > 65535) return cudaErrorInvalidConfiguration;
     if (with_cfar) mtd64_kernel<5, 7, 0, true><<<grid, 128, 0, st>>>(p);
     else mtd64_kernel<5, 7, 0, false><<<grid, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mtd64_tma(const Mtd64Params& p, int n_slabs, int n_sms, cudaStream_t st) {
+    if (p.cols <= 0 || n_slabs <= 0) return cudaSuccess;
+    const int tiles_per_slab = (p.cols + 127) / 128;
+    const long long n_items = (long long)tiles_per_slab * n_slabs;
+    if (n_items > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const size_t smem = 64 * 128 * sizeof(float2);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mtd64_tma_kernel<5, 7, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int grid = (int)std::min<long long>(n_items, (long long)n_sms * RB200_MTD64_MINB);
+    mtd64_tma_kernel<5, 7, 0, true><<<grid, 128, smem, st>>>(p, tiles_per_slab, (int)n_items);
     return cudaGetLastError();
 }
 

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "radix.cuh"
 #include "kernels.h"
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -39,82 +40,14 @@ template <int R, int S> __host__ __device__ constexpr int tw_block_off(int s) {
 
 template <int R, int S, int LT> struct PcOcc { static constexpr int min_blocks = (LT * (ipow(R, S) / R) <= 256) ? 3 : 1; };
 
-template <int R, int S, int LT, bool WIRE, int CFIX>
-__global__ void __launch_bounds__(LT * (ipow(R, S) / R), PcOcc<R, S, LT>::min_blocks)
-pc_fft_kernel(const PcParams p) {
+// Forward DIF -> spectrum multiply -> inverse DIT on the R operands of one thread (see file header).
+// On return v[j] holds lag out_u + j*NB of line out_lane (butterfly-fastest mapping for coalesced stores).
+template <int R, int S, int LT>
+__device__ __forceinline__ void pc_fft_core(float2 (&v)[R], float2* sm, const PcParams& p, const PcSegDev& sg,
+                                            int t, int lane, int u, int& out_lane_r, int& out_u_r) {
     constexpr int NT = ipow(R, S);
-    constexpr int NB = NT / R;     // butterflies per line per stage
-    constexpr int LS = NT + 1;     // line stride in shared memory (odd -> conflict-free across lanes)
-    extern __shared__ float2 sm[];
-
-    const int t = threadIdx.x;
-    const int lane = t % LT;
-    const int u = t / LT;
-    const int2 tile = __ldg(&p.tiles[blockIdx.y]);
-    const PcSegDev& sg = p.segs[tile.x];
-    const int g = blockIdx.x;
-    const int in_off = tile.y * sg.V - sg.pre;
-    const int C = CFIX > 0 ? CFIX : p.C;
-
-    float2 v[R];
-    // ---- stage 0 operands straight from global memory (unpack fused) ----
-    {
-        const int lane_g = blockIdx.z * LT + lane;   // wire: channel index
-        bool lane_ok;
-        long long e0;        // index of the element (range = in_start + in_off + u) of this line
-        int es;              // element stride between consecutive range cells
-        if (WIRE) {
-            lane_ok = lane_g < C;
-            e0 = ((long long)g * p.R + sg.in_start + in_off + u) * C + lane_g;
-            es = C;
-        } else {
-            const int line = g * LT + lane;
-            lane_ok = line < p.n_lines;
-            e0 = (long long)line * p.R + sg.in_start + in_off + u;
-            es = 1;
-        }
-        const bool interior = in_off >= 0 && in_off + NT <= sg.in_len;   // CTA-uniform
-        if (interior && lane_ok) {
-            if (WIRE) {
-                const int* src = reinterpret_cast<const int*>(p.in) + e0;
-                int w[R];
-#pragma unroll
-                for (int j = 0; j < R; ++j) w[j] = __ldg(src + (long long)j * NB * es);
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    v[j].x = (float)(short)(w[j] & 0xffff);   // I (FrameDataRead_xzr.m:154)
-                    v[j].y = (float)(w[j] >> 16);             // Q (:155)
-                }
-            } else {
-                const float2* src = reinterpret_cast<const float2*>(p.in) + e0;
-#pragma unroll
-                for (int j = 0; j < R; ++j) v[j] = __ldg(src + j * NB);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const int rs = in_off + u + j * NB;
-                float2 x = make_float2(0.f, 0.f);
-                if (lane_ok && rs >= 0 && rs < sg.in_len) {
-                    if (WIRE) {
-                        const int w = __ldg(reinterpret_cast<const int*>(p.in) + e0 + (long long)j * NB * es);
-                        x.x = (float)(short)(w & 0xffff);
-                        x.y = (float)(w >> 16);
-                    } else {
-                        x = __ldg(reinterpret_cast<const float2*>(p.in) + e0 + j * NB);
-                    }
-                }
-                v[j] = x;
-            }
-        }
-        if (p.gain) {      // iSTC (MP/fun_iSTC.m:14): per-range gain before compression
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const int rs = in_off + u + j * NB;
-                if (rs >= 0 && rs < sg.in_len) v[j] = cscale(v[j], __ldg(p.gain + sg.in_start + rs));
-            }
-        }
-    }
+    constexpr int NB = NT / R;
+    constexpr int LS = NT + 1;
     float2* line_sm = sm + lane * LS;
 
     // ---- forward DIF ----
@@ -194,6 +127,88 @@ pc_fft_kernel(const PcParams p) {
         }
     }
 
+    out_lane_r = out_lane;
+    out_u_r = out_u;
+}
+
+template <int R, int S, int LT, bool WIRE, int CFIX>
+__global__ void __launch_bounds__(LT * (ipow(R, S) / R), PcOcc<R, S, LT>::min_blocks)
+pc_fft_kernel(const PcParams p) {
+    constexpr int NT = ipow(R, S);
+    constexpr int NB = NT / R;     // butterflies per line per stage
+    extern __shared__ float2 sm[];
+
+    const int t = threadIdx.x;
+    const int lane = t % LT;
+    const int u = t / LT;
+    const int2 tile = __ldg(&p.tiles[blockIdx.y]);
+    const PcSegDev& sg = p.segs[tile.x];
+    const int g = blockIdx.x;
+    const int in_off = tile.y * sg.V - sg.pre;
+    const int C = CFIX > 0 ? CFIX : p.C;
+
+    float2 v[R];
+    // ---- stage 0 operands straight from global memory (unpack fused) ----
+    {
+        const int lane_g = blockIdx.z * LT + lane;   // wire: channel index
+        bool lane_ok;
+        long long e0;        // index of the element (range = in_start + in_off + u) of this line
+        int es;              // element stride between consecutive range cells
+        if (WIRE) {
+            lane_ok = lane_g < C;
+            e0 = ((long long)g * p.R + sg.in_start + in_off + u) * C + lane_g;
+            es = C;
+        } else {
+            const int line = g * LT + lane;
+            lane_ok = line < p.n_lines;
+            e0 = (long long)line * p.R + sg.in_start + in_off + u;
+            es = 1;
+        }
+        const bool interior = in_off >= 0 && in_off + NT <= sg.in_len;   // CTA-uniform
+        if (interior && lane_ok) {
+            if (WIRE) {
+                const int* src = reinterpret_cast<const int*>(p.in) + e0;
+                int w[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) w[j] = __ldg(src + (long long)j * NB * es);
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    v[j].x = (float)(short)(w[j] & 0xffff);   // I (FrameDataRead_xzr.m:154)
+                    v[j].y = (float)(w[j] >> 16);             // Q (:155)
+                }
+            } else {
+                const float2* src = reinterpret_cast<const float2*>(p.in) + e0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) v[j] = __ldg(src + j * NB);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int rs = in_off + u + j * NB;
+                float2 x = make_float2(0.f, 0.f);
+                if (lane_ok && rs >= 0 && rs < sg.in_len) {
+                    if (WIRE) {
+                        const int w = __ldg(reinterpret_cast<const int*>(p.in) + e0 + (long long)j * NB * es);
+                        x.x = (float)(short)(w & 0xffff);
+                        x.y = (float)(w >> 16);
+                    } else {
+                        x = __ldg(reinterpret_cast<const float2*>(p.in) + e0 + j * NB);
+                    }
+                }
+                v[j] = x;
+            }
+        }
+        if (p.gain) {      // iSTC (MP/fun_iSTC.m:14): per-range gain before compression
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int rs = in_off + u + j * NB;
+                if (rs >= 0 && rs < sg.in_len) v[j] = cscale(v[j], __ldg(p.gain + sg.in_start + rs));
+            }
+        }
+    }
+    int out_lane, out_u;
+    pc_fft_core<R, S, LT>(v, sm, p, sg, t, lane, u, out_lane, out_u);
+
     // ---- store the alias-free lags ----
     {
         size_t oline;
@@ -230,6 +245,159 @@ pc_fft_kernel(const PcParams p) {
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant for the wire format with 16 interleaved channels: the raw tile of a work item
+// (NT range cells x 16 channels x 4 B, contiguous in HBM) is fetched by one TMA bulk copy
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) into a double-buffered staging area while
+// the CTA is still transforming the previous item, so the global-load latency never stalls the
+// butterflies.  Grid = resident CTAs (SMs x 3); items (line group, tile) are taken round-robin.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int R, int S>
+__global__ void __launch_bounds__(16 * (ipow(R, S) / R), PcOcc<R, S, 16>::min_blocks)
+pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles) {
+    constexpr int LT = 16;
+    constexpr int NT = ipow(R, S);
+    constexpr int NB = NT / R;
+    constexpr int LS = NT + 1;
+    constexpr int FFT_BYTES = ((LT * LS * (int)sizeof(float2)) + 127) / 128 * 128;
+    constexpr int RAW_INTS = NT * LT;                 // one staged tile: [range][channel] int16 pairs
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* sm = reinterpret_cast<float2*>(smem_raw);
+    int* rawbuf = reinterpret_cast<int*>(smem_raw + FFT_BYTES);
+    __shared__ __align__(8) uint64_t mbar[2];
+
+    const int t = threadIdx.x;
+    const int lane = t % LT;
+    const int u = t / LT;
+    if (t == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // thread 0: start the bulk copy of an item's valid input span into staging buffer `buf`
+    auto issue = [&](int item, int buf) {
+        const int g = item / n_tiles;
+        const int2 tile = __ldg(&p.tiles[item - g * n_tiles]);
+        const PcSegDev& sg = p.segs[tile.x];
+        const int in_off = tile.y * sg.V - sg.pre;
+        const int lo = max(in_off, 0);
+        const int hi = min(in_off + NT, sg.in_len);
+        if (hi > lo) {
+            const uint32_t bytes = (uint32_t)(hi - lo) * (LT * 4);
+            mbar_expect_tx(&mbar[buf], bytes);
+            const int* src = reinterpret_cast<const int*>(p.in) + ((size_t)g * p.R + sg.in_start + lo) * LT;
+            bulk_g2s(rawbuf + buf * RAW_INTS + (lo - in_off) * LT, src, bytes, &mbar[buf]);
+        } else {
+            mbar_arrive(&mbar[buf]);
+        }
+    };
+
+    int item = blockIdx.x;
+    if (t == 0 && item < n_items) issue(item, 0);
+    for (int it = 0; item < n_items; item += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int g = item / n_tiles;
+        const int2 tile = __ldg(&p.tiles[item - g * n_tiles]);
+        const PcSegDev& sg = p.segs[tile.x];
+        const int in_off = tile.y * sg.V - sg.pre;
+
+        mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
+        float2 v[R];
+        {
+            const int* rb = rawbuf + buf * RAW_INTS + u * LT + lane;
+            const bool interior = in_off >= 0 && in_off + NT <= sg.in_len;
+            if (interior) {
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int w = rb[j * NB * LT];
+                    v[j].x = (float)(short)(w & 0xffff);   // I (FrameDataRead_xzr.m:154)
+                    v[j].y = (float)(w >> 16);             // Q (:155)
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int rs = in_off + u + j * NB;
+                    int w = 0;
+                    if (rs >= 0 && rs < sg.in_len) w = rb[j * NB * LT];
+                    v[j].x = (float)(short)(w & 0xffff);
+                    v[j].y = (float)(w >> 16);
+                }
+            }
+            if (p.gain) {
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int rs = in_off + u + j * NB;
+                    if (rs >= 0 && rs < sg.in_len) v[j] = cscale(v[j], __ldg(p.gain + sg.in_start + rs));
+                }
+            }
+        }
+        // the other staging buffer was consumed one iteration ago (every thread has passed a barrier since)
+        {
+            const int next = item + gridDim.x;
+            if (t == 0 && next < n_items) issue(next, buf ^ 1);
+        }
+        int out_lane, out_u;
+        pc_fft_core<R, S, LT>(v, sm, p, sg, t, lane, u, out_lane, out_u);
+        {
+            const int cpi = g / p.P, prt = g - cpi * p.P;
+            const size_t oline = ((size_t)cpi * LT + out_lane) * p.P + prt;
+            const int n0 = tile.y * sg.V;
+            float2* o = p.out + oline * p.R_out + sg.out_start;
+            if (sg.rot == 0) {
+                const int lim = min(sg.V, sg.out_len - n0);
+                o += n0 + out_u;
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+                    if (out_u + j * NB < lim) o[j * NB] = v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int nl = out_u + j * NB;
+                    const int n = n0 + nl;
+                    if (nl < sg.V && n < sg.out_len) {
+                        int c = n - sg.rot;
+                        if (c < 0) c += sg.out_len;
+                        o[c] = v[j];
+                    }
+                }
+            }
+        }
+        __syncthreads();     // the exchange buffer is reused by the next item
     }
 }
 
@@ -337,6 +505,23 @@ void pc_build_twiddles(int nt, std::vector<float2>& tw) {
         Rs *= R;
     }
     if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
+}
+
+cudaError_t launch_pc_fft_tma(const PcParams& p, int n_tiles, int n_groups, int n_sms, cudaStream_t st) {
+    constexpr int R = 16, S = 2, NT = 256, LT = 16;
+    const size_t fft_bytes = ((size_t)LT * (NT + 1) * sizeof(float2) + 127) / 128 * 128;
+    const size_t smem = fft_bytes + 2 * (size_t)NT * LT * 4;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(pc_fft_tma_kernel<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const long long n_items = (long long)n_tiles * n_groups;
+    if (n_items <= 0 || n_items > 0x7fffffffLL) return n_items <= 0 ? cudaSuccess : cudaErrorInvalidConfiguration;
+    const int grid = (int)std::min<long long>(n_items, (long long)n_sms * PcOcc<R, S, LT>::min_blocks);
+    pc_fft_tma_kernel<R, S><<<grid, LT * (NT / R), smem, st>>>(p, (int)n_items, n_tiles);
+    return cudaGetLastError();
 }
 
 int pc_tile_lanes(int nt, bool wire) {
