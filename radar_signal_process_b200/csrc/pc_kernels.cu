@@ -40,11 +40,72 @@ template <int R, int S> __host__ __device__ constexpr int tw_block_off(int s) {
 
 template <int R, int S, int LT> struct PcOcc { static constexpr int min_blocks = (LT * (ipow(R, S) / R) <= 256) ? 3 : 1; };
 
+// One forward DIF stage s >= 1: exchange through shared memory (write at the positions of stage s-1, read at
+// the positions of stage s), butterfly, twiddle.  All strides are template constants.
+template <int R, int S, int s>
+__device__ __forceinline__ void pc_fwd_stage(float2 (&v)[R], float2* line_sm, const float2* __restrict__ twtab, int u) {
+    constexpr int NT = ipow(R, S);
+    constexpr int sp = NT / ipow(R, s);            // stride of stage s-1
+    constexpr int st = NT / ipow(R, s + 1);        // stride of stage s
+    constexpr int twoff = tw_block_off<R, S>(s);
+    const int basep = (u / sp) * sp * R + (u % sp);
+#pragma unroll
+    for (int k = 0; k < R; ++k) line_sm[basep + k * sp] = v[k];
+    __syncthreads();
+    const int q = u % st;
+    const int base = (u / st) * st * R + q;
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = line_sm[base + j * st];
+    Dft<R, -1>::run(v);
+    if (st > 1) {
+        const float2* tw = twtab + twoff + q;
+#pragma unroll
+        for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(tw + k * st));
+    }
+}
+
+// One inverse DIT stage s >= 1: conjugate twiddle, butterfly, exchange towards stage s-1.  When s-1 == 0 the
+// read side is re-mapped butterfly-fastest (out_lane, out_u) so the final stores coalesce along range.
+template <int R, int S, int s, int LT>
+__device__ __forceinline__ void pc_inv_stage(float2 (&v)[R], float2* sm, const float2* __restrict__ twtab, int t, int lane, int u,
+                                             int& out_lane, int& out_u) {
+    constexpr int NT = ipow(R, S);
+    constexpr int NB = NT / R;
+    constexpr int LS = NT + 1;
+    constexpr int st = NT / ipow(R, s + 1);
+    constexpr int sn = NT / ipow(R, s);            // stride of stage s-1
+    constexpr int twoff = tw_block_off<R, S>(s);
+    float2* line_sm = sm + lane * LS;
+    const int q = u % st;
+    if (st > 1) {
+        const float2* tw = twtab + twoff + q;
+#pragma unroll
+        for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], __ldg(tw + k * st));
+    }
+    Dft<R, +1>::run(v);
+    const int base = (u / st) * st * R + q;
+#pragma unroll
+    for (int j = 0; j < R; ++j) line_sm[base + j * st] = v[j];
+    __syncthreads();
+    if (s - 1 == 0) {
+        out_lane = t / NB;
+        out_u = t % NB;
+        const float2* src = sm + out_lane * LS + out_u;
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = src[k * sn];
+    } else {
+        const int basen = (u / sn) * sn * R + (u % sn);
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = line_sm[basen + k * sn];
+    }
+}
+
 // Forward DIF -> spectrum multiply -> inverse DIT on the R operands of one thread (see file header).
 // On return v[j] holds lag out_u + j*NB of line out_lane (butterfly-fastest mapping for coalesced stores).
 template <int R, int S, int LT>
 __device__ __forceinline__ void pc_fft_core(float2 (&v)[R], float2* sm, const PcParams& p, const PcSegDev& sg,
                                             int t, int lane, int u, int& out_lane_r, int& out_u_r) {
+    static_assert(S >= 1 && S <= 3, "1..3 stages");
     constexpr int NT = ipow(R, S);
     constexpr int NB = NT / R;
     constexpr int LS = NT + 1;
@@ -57,25 +118,8 @@ __device__ __forceinline__ void pc_fft_core(float2 (&v)[R], float2* sm, const Pc
 #pragma unroll
         for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(tw + k * NB));
     }
-#pragma unroll
-    for (int s = 1; s < S; ++s) {
-        const int sp = NT / ipow(R, s);           // stride of stage s-1
-        const int basep = (u / sp) * sp * R + (u % sp);
-#pragma unroll
-        for (int k = 0; k < R; ++k) line_sm[basep + k * sp] = v[k];
-        __syncthreads();
-        const int st = NT / ipow(R, s + 1);       // stride of stage s
-        const int q = u % st;
-        const int base = (u / st) * st * R + q;
-#pragma unroll
-        for (int j = 0; j < R; ++j) v[j] = line_sm[base + j * st];
-        Dft<R, -1>::run(v);
-        if (st > 1) {
-            const float2* tw = p.tw + tw_block_off<R, S>(s) + q;
-#pragma unroll
-            for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(tw + k * st));
-        }
-    }
+    if (S >= 2) pc_fwd_stage<R, S, 1>(v, line_sm, p.tw, u);
+    if (S >= 3) pc_fwd_stage<R, S, (S >= 3 ? 2 : 1)>(v, line_sm, p.tw, u);
 
     // ---- reference spectrum (digit-reversed order == this thread's positions u*R .. u*R+R-1) ----
     {
@@ -90,43 +134,15 @@ __device__ __forceinline__ void pc_fft_core(float2 (&v)[R], float2* sm, const Pc
 
     // ---- inverse DIT ----
     int out_lane = lane, out_u = u;
+    if (S >= 3) pc_inv_stage<R, S, (S >= 3 ? 2 : 1), LT>(v, sm, p.tw, t, lane, u, out_lane, out_u);
+    if (S >= 2) pc_inv_stage<R, S, 1, LT>(v, sm, p.tw, t, lane, u, out_lane, out_u);
+    if (S > 1) {
+        // stage 0 (operands fetched with the store mapping)
+        const float2* tw = p.tw + out_u;
 #pragma unroll
-    for (int s = S - 1; s >= 0; --s) {
-        const int st = NT / ipow(R, s + 1);
-        const int q = u % st;
-        if (st > 1 && s > 0) {
-            const float2* tw = p.tw + tw_block_off<R, S>(s) + q;
-#pragma unroll
-            for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], __ldg(tw + k * st));
-        }
-        if (s == 0 && S > 1) {
-            // stage-0 operands were fetched with the store mapping (out_lane, out_u)
-            const float2* tw = p.tw + out_u;
-#pragma unroll
-            for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], __ldg(tw + k * NB));
-        }
-        Dft<R, +1>::run(v);
-        if (s > 0) {
-            const int base = (u / st) * st * R + q;
-#pragma unroll
-            for (int j = 0; j < R; ++j) line_sm[base + j * st] = v[j];
-            __syncthreads();
-            const int sn = NT / ipow(R, s);       // stride of stage s-1
-            if (s - 1 == 0) {
-                // re-map: butterfly index fastest so that global stores coalesce along range
-                out_lane = t / NB;
-                out_u = t % NB;
-                const float2* src = sm + out_lane * LS + out_u;
-#pragma unroll
-                for (int k = 0; k < R; ++k) v[k] = src[k * sn];
-            } else {
-                const int basen = (u / sn) * sn * R + (u % sn);
-#pragma unroll
-                for (int k = 0; k < R; ++k) v[k] = line_sm[basen + k * sn];
-            }
-        }
+        for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], __ldg(tw + k * NB));
     }
-
+    Dft<R, +1>::run(v);
     out_lane_r = out_lane;
     out_u_r = out_u;
 }
