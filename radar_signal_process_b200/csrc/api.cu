@@ -930,9 +930,10 @@ static int chunk_size(const rb200_ctx* c) {
     const char* env = getenv("RB200_CHUNK");
     int g = env ? atoi(env) : c->cfg.chunk_cpi;
     if (g <= 0) {
-        // default: a few tens of MB of PC intermediate per chunk (S3: 4 CPIs); measured flat between 2 and 8
+        // default: ~0.5 GB of raw+PC+RDM per chunk (S3: 8 CPIs).  Measured on B200: per-launch overheads dominate below
+        // 4 CPIs per chunk and the PC intermediate is not L2-resident at any practical chunk size (profiles/README.md)
         const double per_cpi = (double)c->cfg.n_prt * c->cfg.n_range * c->cfg.n_lanes * 16.0;
-        g = (int)std::floor(280e6 / per_cpi);
+        g = (int)std::floor(540e6 / per_cpi);
     }
     return std::max(1, std::min(g, c->cfg.max_cpi));
 }

@@ -46,51 +46,53 @@ __device__ __forceinline__ bool cfar_decide(const T* __restrict__ base, ptrdiff_
     return base[(ptrdiff_t)y * stride] >= mu * thr;
 }
 
-// Stage V.  Thread <-> one cell; 32 consecutive threads share a row (row-major) so the ballot word is
-// one mask word.  ROWMAJOR: element (v,r) at v*R + r (float chain).  Otherwise column-major v + V*r.
+// Stage V.  One thread walks down one range column (rows [v_lo, v_hi), split over blockIdx.z into row
+// segments): consecutive rows re-use 9 of the 10 reference rows from L1, every global access is a
+// 128-byte row segment shared by the warp, and the 32 decisions of a warp for one row form one mask word
+// (__ballot_sync).  ROWMAJOR: element (v,r) at v*R + r (float chain); otherwise column-major v + V*r.
 template <typename T, bool ROWMAJOR>
-__global__ void cfar_v_kernel(const T* __restrict__ rdm, const CfarParams p, T t_v, int n_slabs,
+__global__ void cfar_v_kernel(const T* __restrict__ rdm, const CfarParams p, T t_v, int rows_per_seg,
                               rb200_det* __restrict__ dets, int* __restrict__ det_count,
                               uint32_t* __restrict__ vmask, uint8_t* __restrict__ flagv, int* err_flag) {
     const int Rw = (p.R + 31) / 32;
     const int nv = p.v_hi - p.v_lo;
-    const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    const int slab = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;      // blockDim.x is a multiple of 32
     const int lane = threadIdx.x & 31;
-    const size_t total_words = (size_t)n_slabs * nv * Rw;
-    if (warp_global >= total_words) return;
-    const int word = (int)(warp_global % Rw);
-    const size_t t1 = warp_global / Rw;
-    const int vi = (int)(t1 % nv);
-    const int slab = (int)(t1 / nv);
-    const int r = word * 32 + lane;
-    const int v = p.v_lo + vi;
-    bool hit = false;
-    T amp = 0;
-    if (r < p.R) {
-        const T* slab_base = rdm + (size_t)slab * p.V * p.R;
-        const T* col = ROWMAJOR ? slab_base + (size_t)p.v_lo * p.R + r : slab_base + p.v_lo + (size_t)p.V * r;
-        const ptrdiff_t sv = ROWMAJOR ? p.R : 1;
-        hit = cfar_decide<T>(col, sv, vi, nv, p.ref_v, p.guard_v, t_v, p.meth_v, err_flag);
-        if (hit) amp = col[(ptrdiff_t)vi * sv];
-    }
-    const unsigned ball = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) vmask[((size_t)slab * p.V + v) * Rw + word] = ball;
-    if (flagv && hit) flagv[ROWMAJOR ? ((size_t)slab * p.V + v) * p.R + r : (size_t)slab * p.V * p.R + v + (size_t)p.V * r] = 1;
-    if (ball == 0) return;
-    int basei = 0;
-    if (lane == 0) basei = atomicAdd(det_count, __popc(ball));
-    basei = __shfl_sync(0xffffffffu, basei, 0);
-    if (hit) {
-        const int slot = basei + __popc(ball & ((1u << lane) - 1u));
-        if (slot < p.max_det) {
-            rb200_det d;
-            d.cpi = (uint32_t)(p.cpi0 + slab / p.n_lanes);
-            d.r = (uint32_t)r;
-            d.v = (uint16_t)v;
-            d.lane = (uint8_t)(slab % p.n_lanes);
-            d.kind = RB200_DET_V;
-            d.amp = (float)amp;
-            dets[slot] = d;
+    const int word = r >> 5;
+    const bool in_range = r < p.R;
+    const T* slab_base = rdm + (size_t)slab * p.V * p.R;
+    const T* col = ROWMAJOR ? slab_base + (size_t)p.v_lo * p.R + (in_range ? r : 0) : slab_base + p.v_lo + (size_t)p.V * (in_range ? r : 0);
+    const ptrdiff_t sv = ROWMAJOR ? p.R : 1;
+    const int y0 = blockIdx.z * rows_per_seg;
+    const int y1 = min(nv, y0 + rows_per_seg);
+    for (int vi = y0; vi < y1; ++vi) {
+        const int v = p.v_lo + vi;
+        bool hit = false;
+        T amp = 0;
+        if (in_range) {
+            hit = cfar_decide<T>(col, sv, vi, nv, p.ref_v, p.guard_v, t_v, p.meth_v, err_flag);
+            if (hit) amp = col[(ptrdiff_t)vi * sv];
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0 && word < Rw) vmask[((size_t)slab * p.V + v) * Rw + word] = ball;
+        if (ball == 0) continue;
+        if (flagv && hit) flagv[ROWMAJOR ? ((size_t)slab * p.V + v) * p.R + r : (size_t)slab * p.V * p.R + v + (size_t)p.V * r] = 1;
+        int basei = 0;
+        if (lane == 0) basei = atomicAdd(det_count, __popc(ball));
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        if (hit) {
+            const int slot = basei + __popc(ball & ((1u << lane) - 1u));
+            if (slot < p.max_det) {
+                rb200_det d;
+                d.cpi = (uint32_t)(p.cpi0 + slab / p.n_lanes);
+                d.r = (uint32_t)r;
+                d.v = (uint16_t)v;
+                d.lane = (uint8_t)(slab % p.n_lanes);
+                d.kind = RB200_DET_V;
+                d.amp = (float)amp;
+                dets[slot] = d;
+            }
         }
     }
 }
@@ -177,9 +179,15 @@ static cudaError_t run_cfar(const T* rdm, const CfarParams& p, T t_r, T t_v, int
     const int Rw = (p.R + 31) / 32;
     const int nv = p.v_hi - p.v_lo;
     if (nv <= 0 || n_slabs <= 0) return cudaSuccess;
-    const size_t words = (size_t)n_slabs * nv * Rw;
-    const size_t threads = words * 32;
-    cfar_v_kernel<T, ROWMAJOR><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(rdm, p, t_v, n_slabs, dets_v, count_v, vmask, flagv, err_flag);
+    (void)Rw;
+    if (n_slabs > 65535) return cudaErrorInvalidConfiguration;
+    // enough row segments to fill the machine when columns x slabs alone are few
+    const int col_blocks = (p.R + 127) / 128;
+    int segs = 1;
+    while ((long long)col_blocks * n_slabs * segs < 1184 && nv / (segs * 2) >= 16 && segs < 64) segs *= 2;
+    const int rows_per_seg = (nv + segs - 1) / segs;
+    dim3 grid(col_blocks, n_slabs, (nv + rows_per_seg - 1) / rows_per_seg);
+    cfar_v_kernel<T, ROWMAJOR><<<grid, 128, 0, st>>>(rdm, p, t_v, rows_per_seg, dets_v, count_v, vmask, flagv, err_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (p.range_stage) {
