@@ -96,7 +96,8 @@ typedef struct {
 } rb200_segment;
 
 /* One detection.  kind bit0 = velocity-stage hit (cfarResultFlag_MatrixV), bit1 = final 2-D flag
- * (cfarResultFlag_Matrix).  v and r are 0-based; the gateways add 1 for MATLAB.                   */
+ * (cfarResultFlag_Matrix).  A cell may appear in two records (one per bit); with the range stage off
+ * every velocity hit carries both bits (CW/executeCFAR.m:91).  v and r are 0-based.               */
 typedef struct {
     uint32_t cpi;
     uint32_t r;

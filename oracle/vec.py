@@ -193,7 +193,8 @@ def cfar1d_last(data, ref, guard, T, method, want_margin=False):
     flags = (data >= thr).astype(np.float64)
     if not want_margin:
         return flags
-    margin = np.abs(data - thr) / np.maximum(np.abs(thr), np.finfo(np.float64).tiny)
+    with np.errstate(over="ignore"):
+        margin = np.abs(data - thr) / np.maximum(np.abs(thr), np.finfo(np.float64).tiny)
     return flags, margin
 
 

@@ -89,7 +89,7 @@ __global__ void cfar_v_kernel(const T* __restrict__ rdm, const CfarParams p, T t
                 d.r = (uint32_t)r;
                 d.v = (uint16_t)v;
                 d.lane = (uint8_t)(slab % p.n_lanes);
-                d.kind = RB200_DET_V;
+                d.kind = p.range_stage ? RB200_DET_V : (RB200_DET_V | RB200_DET_2D);   // executeCFAR.m:91
                 d.amp = (float)amp;
                 dets[slot] = d;
             }

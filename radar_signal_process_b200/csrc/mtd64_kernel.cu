@@ -267,7 +267,8 @@ __global__ void cfar_r64_kernel(const float* __restrict__ rdm, const CfarParams 
     const int true_n = n;
     if (n > p.max_det) n = p.max_det;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const rb200_det h = slot_v[i];
+        rb200_det h = slot_v[i];
+        if (!p.range_stage) h.kind = RB200_DET_V | RB200_DET_2D;   // executeCFAR.m:91: the final matrix IS the velocity matrix
         {
             const int slot = atomicAdd(&gcount[0], 1);
             if (slot < p.max_det) dets_v[slot] = h;

@@ -361,3 +361,52 @@ def test_chain_detection_overflow_is_reported(lib):
             ctx.chain(raw, B)
         rdm, dets, n = ctx.chain(raw, B, allow_overflow=True)
         assert n > 1000 and len(dets) == 1000
+
+
+@pytest.mark.parametrize("case", [
+    # P,  R,    C, B, cfar (refR,gR,T_R,mR, refV,gV,T_V,mV, n0, rflag), mti, zero_div, chunk
+    dict(P=64, R=1000, C=1, B=3, cfar=(5, 7, 5.0, 0, 5, 7, 5.0, 0, 0, 1), mti=0, zdiv=150, chunk=2),    # single lane, ragged R, fused path
+    dict(P=64, R=777, C=20, B=1, cfar=(5, 7, 4.0, 1, 5, 7, 4.0, 1, 0, 1), mti=0, zdiv=20, chunk=1),     # >16 lanes (two lane groups), SO-CFAR, odd R
+    dict(P=64, R=512, C=3, B=2, cfar=(3, 2, 4.0, 0, 4, 3, 4.0, 0, 2, 1), mti=0, zdiv=150, chunk=1),     # non-default windows + n0 -> unfused path
+    dict(P=64, R=640, C=2, B=2, cfar=(5, 7, 5.0, 0, 5, 7, 5.0, 0, 0, 0), mti=0, zdiv=150, chunk=2),     # range stage off
+    dict(P=64, R=512, C=2, B=1, cfar=(5, 7, 5.0, 0, 5, 7, 5.0, 0, 0, 1), mti=30, zdiv=150, chunk=1),    # MTI on P=64 -> shared-memory MTD path
+    dict(P=128, R=384, C=2, B=1, cfar=(5, 7, 5.0, 0, 5, 7, 5.0, 0, 1, 1), mti=0, zdiv=150, chunk=1),    # generic Stockham Doppler length
+    dict(P=48, R=300, C=2, B=2, cfar=(5, 7, 5.0, 0, 4, 3, 5.0, 0, 0, 1), mti=0, zdiv=0, chunk=2),       # P = 2^4*3, no zero-velocity mask
+])
+def test_chain_variants(lib, case):
+    P, R, C, B = case["P"], case["R"], case["C"], case["B"]
+    ref = mcode.load_ref("refDDCDataMF1")
+    raw, _ = synth.s3_batch(B, P=P, R=R, C=C, n_targets=3, r_lo=20, r_hi=R - 80)
+    if case["zdiv"]:
+        out = vec.chain(raw, B, P, R, C, ("single", ref), case["cfar"], zero_div=case["zdiv"], mti_lag=case["mti"], near_tol=RTOL)
+    else:
+        x = vec.single_pc(vec.unpack_wire(raw, B, P, R, C), ref)
+        rdm0 = vec.process_mtd(x)
+        res = vec.execute_cfar(rdm0, *case["cfar"], near_tol=RTOL)
+        out = {"rdm": rdm0, "flag": res[0], "flagV": res[1], "near": res[2], "nearV": res[3]}
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), case["cfar"], mti_lag=case["mti"], zero_v_div=case["zdiv"],
+                    chunk_cpi=case["chunk"], max_det=1 << 20) as ctx:
+        rdm, dets, n = ctx.chain(raw, B)
+    _close(rdm, out["rdm"])
+    _compare_flags(dets, out, B, C, P, R, lib)
+    if not case["cfar"][-1]:        # rCFARDetect_Flag = 0: every velocity hit is also the final flag (executeCFAR.m:91)
+        assert (dets["kind"] == (lib.DET_V | lib.DET_2D)).all()
+
+
+def test_chain_argument_errors(lib):
+    ref = mcode.load_ref("refDDCDataMF1")
+    with lib.Context(0, n_prt=64, n_range=256, n_lanes=2, max_cpi=2) as ctx:
+        raw = np.zeros((1, 64, 256, 2, 2), dtype=np.int16)
+        with pytest.raises(lib.RadarB200Error) as e:          # no waveform yet
+            ctx.chain(raw, 1)
+        assert e.value.status == 5
+        ctx.set_waveform(lib.waveforms.segments_single(512, ref))   # plan longer than the PRT
+        with pytest.raises(lib.MatlabIndexError):
+            ctx.chain(raw, 1)
+        ctx.set_waveform(lib.waveforms.segments_single(256, ref))
+        with pytest.raises(lib.RadarB200Error):               # n_cpi > max_cpi
+            ctx.chain(np.zeros((3, 64, 256, 2, 2), dtype=np.int16), 3)
+    with lib.Context(0, n_prt=16, n_range=256, n_lanes=1, max_cpi=1) as ctx:   # 15 tested rows < 2*(5+7)
+        ctx.set_waveform(lib.waveforms.segments_single(256, ref))
+        with pytest.raises(lib.MatlabIndexError):
+            ctx.chain(np.ones((1, 16, 256, 1, 2), dtype=np.int16), 1)
