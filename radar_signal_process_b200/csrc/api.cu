@@ -150,6 +150,9 @@ struct rb200_ctx {
     // chain buffers
     DevBuf raw, pc, rdm, dets_v, dets_2d, counters, vmask, errflag, colmask;
     int n_sms = 148;
+    // persistent-grid sizing (CTAs per SM): 3/3 fills the SM with one kernel at a time; 2/1 lets the compute-bound PC
+    // kernel of chunk i+1 and the HBM-bound MTD kernel of chunk i be co-resident (registers: 2*20.5K + 19.6K <= 64K)
+    int pc_ctas_per_sm = 3, mtd_ctas_per_sm = 3;
     // chunk pipelining of the fused path: chunk i runs on slot i % n_slots (own stream + scratch), so the
     // tail of one chunk's kernels overlaps the head of the next while the PC intermediate stays L2-sized
     struct Slot {
@@ -379,7 +382,7 @@ static int run_pc(rb200_ctx* ctx, const Plan& plan, bool wire, const void* in, f
         const int lt = pc_tile_lanes(c.nt, wire);
         const int n_groups = wire ? n_groups_wire : (n_lines + lt - 1) / lt;
         if (n_groups <= 0) continue;
-        if (wire && C == 16 && c.nt == 256 && !getenv("RB200_NO_TMA")) CK(ctx, launch_pc_fft_tma(p, c.n_tiles, n_groups, ctx->n_sms, st));
+        if (wire && C == 16 && c.nt == 256 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && !getenv("RB200_NO_TMA")) CK(ctx, launch_pc_fft_tma(p, c.n_tiles, n_groups, ctx->n_sms, ctx->pc_ctas_per_sm, st));
         else CK(ctx, launch_pc_fft(c.nt, wire, p, c.n_tiles, n_groups, st));
         ctx->launches++;
     }
@@ -533,6 +536,8 @@ extern "C" int rb200_create(rb200_ctx** out, int device, const rb200_config* cfg
     }
     if (validate_cfar(c, k)) { g_create_error = c->err; delete c; return RB200_ERR_ARG; }
     cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device);
+    if (const char* e1 = getenv("RB200_PC_CTAS")) c->pc_ctas_per_sm = atoi(e1);
+    if (const char* e2 = getenv("RB200_MTD_CTAS")) c->mtd_ctas_per_sm = atoi(e2);
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
@@ -1038,7 +1043,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
             m64.dets = sl.vlist.p;
             m64.det_count = sl.count.as<int>();
             m64.colmask = sl.colmask.as<unsigned long long>();
-            if ((R % 2) == 0 && !getenv("RB200_NO_TMA_MTD")) CK(c, launch_mtd64_tma(m64, g * C, c->n_sms, cs));
+            if ((R % 2) == 0 && !getenv("RB200_NO_TMA_MTD")) CK(c, launch_mtd64_tma(m64, g * C, c->n_sms, c->mtd_ctas_per_sm, cs));
             else CK(c, launch_mtd64(m64, g * C, true, cs));
             c->launches++;
             if (timed) stage_event(c, cs);

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "../../include/radar_b200.h"
+#include <cstdlib>
 
 namespace rb {
 
@@ -92,6 +93,66 @@ __global__ void cfar_v_kernel(const T* __restrict__ rdm, const CfarParams p, T t
                 d.kind = p.range_stage ? RB200_DET_V : (RB200_DET_V | RB200_DET_2D);   // executeCFAR.m:91
                 d.amp = (float)amp;
                 dets[slot] = d;
+            }
+        }
+    }
+}
+
+// Stage V for the float chain with the reference rows staged through shared memory: a CTA owns 128 range
+// columns and walks down the velocity axis in chunks of 32 rows; each chunk (plus ref+guard halo rows on both
+// sides) is loaded once with 512-byte coalesced row segments, then every thread decides its 32 cells from
+// shared memory.  HBM/L2 traffic drops from 11 loads per cell to (32+2H)/32.
+#define RB_CFAR_TILE_ROWS 32
+__global__ void __launch_bounds__(128)
+cfar_v_tiled_kernel(const float* __restrict__ rdm, const CfarParams p, float t_v, int rows_per_seg,
+                    rb200_det* __restrict__ dets, int* __restrict__ det_count, uint32_t* __restrict__ vmask, int* err_flag) {
+    extern __shared__ float tile[];                 // [(32 + 2H)][128]
+    const int H = p.ref_v + p.guard_v;
+    const int Rw = (p.R + 31) / 32;
+    const int nv = p.v_hi - p.v_lo;
+    const int slab = blockIdx.y;
+    const int r = blockIdx.x * 128 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int word = r >> 5;
+    const bool in_range = r < p.R;
+    const float* col = rdm + ((size_t)slab * p.V + p.v_lo) * p.R + (in_range ? r : 0);
+    const int y_begin = blockIdx.z * rows_per_seg;
+    const int y_end = min(nv, y_begin + rows_per_seg);
+    for (int y0 = y_begin; y0 < y_end; y0 += RB_CFAR_TILE_ROWS) {
+        const int lo = max(0, y0 - H);
+        const int hi = min(nv, y0 + RB_CFAR_TILE_ROWS + H);
+        __syncthreads();                            // previous chunk fully consumed
+        if (in_range)
+            for (int y = lo; y < hi; ++y) tile[(y - lo) * 128 + threadIdx.x] = __ldg(col + (size_t)y * p.R);
+        __syncthreads();
+        const float* scol = tile + threadIdx.x - lo * 128;      // scol[y*128] == x[y][r] for y in [lo, hi)
+        const int y1 = min(y_end, y0 + RB_CFAR_TILE_ROWS);
+        for (int vi = y0; vi < y1; ++vi) {
+            const int v = p.v_lo + vi;
+            bool hit = false;
+            float amp = 0.f;
+            if (in_range) {
+                hit = cfar_decide<float>(scol, 128, vi, nv, p.ref_v, p.guard_v, t_v, p.meth_v, err_flag);
+                if (hit) amp = scol[vi * 128];
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0 && word < Rw) vmask[((size_t)slab * p.V + v) * Rw + word] = ball;
+            if (ball == 0) continue;
+            int basei = 0;
+            if (lane == 0) basei = atomicAdd(det_count, __popc(ball));
+            basei = __shfl_sync(0xffffffffu, basei, 0);
+            if (hit) {
+                const int slot = basei + __popc(ball & ((1u << lane) - 1u));
+                if (slot < p.max_det) {
+                    rb200_det d;
+                    d.cpi = (uint32_t)(p.cpi0 + slab / p.n_lanes);
+                    d.r = (uint32_t)r;
+                    d.v = (uint16_t)v;
+                    d.lane = (uint8_t)(slab % p.n_lanes);
+                    d.kind = p.range_stage ? RB200_DET_V : (RB200_DET_V | RB200_DET_2D);   // executeCFAR.m:91
+                    d.amp = amp;
+                    dets[slot] = d;
+                }
             }
         }
     }
@@ -187,7 +248,16 @@ static cudaError_t run_cfar(const T* rdm, const CfarParams& p, T t_r, T t_v, int
     while ((long long)col_blocks * n_slabs * segs < 1184 && nv / (segs * 2) >= 16 && segs < 64) segs *= 2;
     const int rows_per_seg = (nv + segs - 1) / segs;
     dim3 grid(col_blocks, n_slabs, (nv + rows_per_seg - 1) / rows_per_seg);
-    cfar_v_kernel<T, ROWMAJOR><<<grid, 128, 0, st>>>(rdm, p, t_v, rows_per_seg, dets_v, count_v, vmask, flagv, err_flag);
+    const int H = p.ref_v + p.guard_v;
+    if (ROWMAJOR && sizeof(T) == 4 && !flagv && H <= 48 && !getenv("RB200_NO_CFAR_TILE")) {
+        const size_t smem = (size_t)(RB_CFAR_TILE_ROWS + 2 * H) * 128 * sizeof(float);
+        static size_t configured[64] = {};
+        cudaError_t ce = ensure_dynamic_smem(cfar_v_tiled_kernel, smem, configured);
+        if (ce != cudaSuccess) return ce;
+        cfar_v_tiled_kernel<<<grid, 128, smem, st>>>(reinterpret_cast<const float*>(rdm), p, (float)t_v, rows_per_seg, dets_v, count_v, vmask, err_flag);
+    } else {
+        cfar_v_kernel<T, ROWMAJOR><<<grid, 128, 0, st>>>(rdm, p, t_v, rows_per_seg, dets_v, count_v, vmask, flagv, err_flag);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (p.range_stage) {

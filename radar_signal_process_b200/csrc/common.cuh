@@ -9,6 +9,19 @@ constexpr int kMaxSegs = 8;
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember the largest size configured on each.
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K kernel, size_t bytes, size_t (&done)[64]) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    dev &= 63;
+    if (bytes <= done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done[dev] = bytes;
+    return e;
+}
+
 // One waveform segment in correlation form:
 //   y[n] = sum_k xin[n + k - pre] * conj(t[k]),  n in [0, out_len),  xin = 0 outside [0, in_len)
 //   out[out_start + ((n - rot) mod out_len)] = y[n]

@@ -326,19 +326,17 @@ cudaError_t launch_mtd64(const Mtd64Params& p, int n_slabs, bool with_cfar, cuda
     return cudaGetLastError();
 }
 
-cudaError_t launch_mtd64_tma(const Mtd64Params& p, int n_slabs, int n_sms, cudaStream_t st) {
+cudaError_t launch_mtd64_tma(const Mtd64Params& p, int n_slabs, int n_sms, int ctas_per_sm, cudaStream_t st) {
     if (p.cols <= 0 || n_slabs <= 0) return cudaSuccess;
     const int tiles_per_slab = (p.cols + 127) / 128;
     const long long n_items = (long long)tiles_per_slab * n_slabs;
     if (n_items > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const size_t smem = 64 * 128 * sizeof(float2);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mtd64_tma_kernel<5, 7, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    const int grid = (int)std::min<long long>(n_items, (long long)n_sms * RB200_MTD64_MINB);
+    static size_t configured[64] = {};
+    cudaError_t ce = ensure_dynamic_smem(mtd64_tma_kernel<5, 7, 0, true>, smem, configured);
+    if (ce != cudaSuccess) return ce;
+    const int per_sm = std::max(1, std::min(ctas_per_sm, RB200_MTD64_MINB));
+    const int grid = (int)std::min<long long>(n_items, (long long)n_sms * per_sm);
     mtd64_tma_kernel<5, 7, 0, true><<<grid, 128, smem, st>>>(p, tiles_per_slab, (int)n_items);
     return cudaGetLastError();
 }

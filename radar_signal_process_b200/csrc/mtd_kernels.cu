@@ -137,12 +137,9 @@ template <int R, int TR>
 static cudaError_t launch_fast(const MtdParams& p, int n_slabs, cudaStream_t st) {
     constexpr int P = R * R;
     const size_t smem = (size_t)P * TR * sizeof(float2);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mtd_fast_kernel<R, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static size_t configured[64] = {};
+    cudaError_t ce = ensure_dynamic_smem(mtd_fast_kernel<R, TR>, smem, configured);
+    if (ce != cudaSuccess) return ce;
     dim3 grid((p.cols + TR - 1) / TR, n_slabs, 1);
     if (n_slabs > 65535) return cudaErrorInvalidConfiguration;
     mtd_fast_kernel<R, TR><<<grid, TR * R, smem, st>>>(p);
@@ -158,12 +155,9 @@ cudaError_t launch_mtd(const MtdParams& p, int n_slabs, cudaStream_t st) {
     while (TR > 1 && (size_t)2 * p.P * TR * sizeof(float2) > 96 * 1024) TR >>= 1;
     const size_t smem = (size_t)2 * p.P * TR * sizeof(float2);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(mtd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static size_t configured[64] = {};
+    cudaError_t ce = ensure_dynamic_smem(mtd_generic_kernel, smem, configured);
+    if (ce != cudaSuccess) return ce;
     dim3 block(TR, 256 / TR, 1);
     dim3 grid((p.cols + TR - 1) / TR, n_slabs, 1);
     if (n_slabs > 65535) return cudaErrorInvalidConfiguration;

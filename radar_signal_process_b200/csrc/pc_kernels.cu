@@ -492,12 +492,9 @@ static cudaError_t launch_fft(const PcParams& p, int n_tiles, int n_groups, cuda
     constexpr int NT = ipow(R, S);
     constexpr int threads = LT * (NT / R);
     const size_t smem = (size_t)LT * (NT + 1) * sizeof(float2);
-    static bool configured = false;   // per template instantiation
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(pc_fft_kernel<R, S, LT, WIRE, CFIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static size_t configured[64] = {};   // per template instantiation and device
+    cudaError_t ce = ensure_dynamic_smem(pc_fft_kernel<R, S, LT, WIRE, CFIX>, smem, configured);
+    if (ce != cudaSuccess) return ce;
     dim3 grid(n_groups, n_tiles, WIRE ? (p.C + LT - 1) / LT : 1);
     if (n_tiles > 65535) return cudaErrorInvalidConfiguration;
     pc_fft_kernel<R, S, LT, WIRE, CFIX><<<grid, threads, smem, st>>>(p);
@@ -523,19 +520,17 @@ void pc_build_twiddles(int nt, std::vector<float2>& tw) {
     if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
 }
 
-cudaError_t launch_pc_fft_tma(const PcParams& p, int n_tiles, int n_groups, int n_sms, cudaStream_t st) {
+cudaError_t launch_pc_fft_tma(const PcParams& p, int n_tiles, int n_groups, int n_sms, int ctas_per_sm, cudaStream_t st) {
     constexpr int R = 16, S = 2, NT = 256, LT = 16;
     const size_t fft_bytes = ((size_t)LT * (NT + 1) * sizeof(float2) + 127) / 128 * 128;
     const size_t smem = fft_bytes + 2 * (size_t)NT * LT * 4;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(pc_fft_tma_kernel<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static size_t configured[64] = {};
+    cudaError_t ce = ensure_dynamic_smem(pc_fft_tma_kernel<R, S>, smem, configured);
+    if (ce != cudaSuccess) return ce;
     const long long n_items = (long long)n_tiles * n_groups;
     if (n_items <= 0 || n_items > 0x7fffffffLL) return n_items <= 0 ? cudaSuccess : cudaErrorInvalidConfiguration;
-    const int grid = (int)std::min<long long>(n_items, (long long)n_sms * PcOcc<R, S, LT>::min_blocks);
+    const int per_sm = std::max(1, std::min(ctas_per_sm, (int)PcOcc<R, S, LT>::min_blocks));
+    const int grid = (int)std::min<long long>(n_items, (long long)n_sms * per_sm);
     pc_fft_tma_kernel<R, S><<<grid, LT * (NT / R), smem, st>>>(p, (int)n_items, n_tiles);
     return cudaGetLastError();
 }
