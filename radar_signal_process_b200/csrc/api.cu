@@ -112,6 +112,7 @@ struct Plan {
     std::vector<SegPlan> segs;
     std::vector<ClassPlan> classes;
     DevBuf hperm, taps;
+    int h_entries = 0;             // float2 entries in hperm
     std::vector<std::pair<int, int>> out_ranges;   // sorted [start, end) written by segments
     int max_in_end = 0, max_out_end = 0;
     bool valid = false;
@@ -149,6 +150,8 @@ struct rb200_ctx {
     int gain_n = 0;
     // chain buffers
     DevBuf raw, pc, rdm, dets_v, dets_2d, counters, vmask, errflag, colmask;
+    DevBuf ring, megactr;          // fused persistent chain: L2-resident PC ring, work / completion counters
+    bool last_was_mega = false;
     int n_sms = 148;
     // persistent-grid sizing (CTAs per SM): 3/3 fills the SM with one kernel at a time; 2/1 lets the compute-bound PC
     // kernel of chunk i+1 and the HBM-bound MTD kernel of chunk i be co-resident (registers: 2*20.5K + 19.6K <= 64K)
@@ -319,6 +322,7 @@ static int build_plan(rb200_ctx* ctx, Plan& plan, const rb200_segment* segs, int
             hperm[sp.d.h_off + pos] = make_float2((float)h.real(), (float)h.imag());
         }
     }
+    plan.h_entries = (int)h_total;
     CK(ctx, plan.hperm.ensure(hperm.size() * sizeof(float2)));
     CK(ctx, cudaMemcpyAsync(plan.hperm.p, hperm.data(), hperm.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, plan.taps.ensure(std::max<size_t>(taps_all.size(), 1) * sizeof(float2)));
@@ -382,7 +386,8 @@ static int run_pc(rb200_ctx* ctx, const Plan& plan, bool wire, const void* in, f
         const int lt = pc_tile_lanes(c.nt, wire);
         const int n_groups = wire ? n_groups_wire : (n_lines + lt - 1) / lt;
         if (n_groups <= 0) continue;
-        if (wire && C == 16 && c.nt == 256 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && !getenv("RB200_NO_TMA")) CK(ctx, launch_pc_fft_tma(p, c.n_tiles, n_groups, ctx->n_sms, ctx->pc_ctas_per_sm, st));
+        if (wire && C == 16 && c.nt == 256 && plan.h_entries <= 2048 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && !getenv("RB200_NO_TMA"))
+            CK(ctx, launch_pc_fft_tma(p, c.n_tiles, n_groups, ctx->n_sms, ctx->pc_ctas_per_sm, plan.h_entries, st));
         else CK(ctx, launch_pc_fft(c.nt, wire, p, c.n_tiles, n_groups, st));
         ctx->launches++;
     }
@@ -570,7 +575,7 @@ extern "C" int rb200_destroy(rb200_ctx* c) {
         kv.second->tw.release();
         delete kv.second;
     }
-    DevBuf* bufs[] = {&c->gain, &c->raw, &c->pc, &c->rdm, &c->dets_v, &c->dets_2d, &c->counters, &c->vmask, &c->errflag, &c->colmask,
+    DevBuf* bufs[] = {&c->gain, &c->raw, &c->pc, &c->rdm, &c->dets_v, &c->dets_2d, &c->counters, &c->vmask, &c->errflag, &c->colmask, &c->ring, &c->megactr,
                       &c->s_in_re, &c->s_in_im, &c->s_a, &c->s_b, &c->s_c, &c->s_out_re, &c->s_out_im, &c->s_u8a, &c->s_u8b, &c->s_idx};
     for (DevBuf* b : bufs) b->release();
     if (c->h_dets) cudaFreeHost(c->h_dets);
@@ -977,6 +982,84 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     Mtd64Params m64;
     memset(&m64, 0, sizeof m64);
     int n_slots = 1;
+    c->last_was_mega = false;
+    // ---- fused persistent kernel for the whole batch (chain64_kernel.cu): device-resident input and output, 16 channels,
+    //      one 256-sample tile class covering the whole PRT
+    if (fused && raw_dev && rdm_dev && !raw_host && !rdm_host && C == 16 && c->plan.valid && c->plan.classes.size() == 1 &&
+        c->plan.classes[0].nt == 256 && c->plan.max_in_end <= R && c->plan.max_out_end <= R && (reinterpret_cast<uintptr_t>(raw_dev) & 15) == 0 &&
+        getenv("RB200_MEGA")) {      // opt-in: measured slower than the slot pipeline on B200 (profiles/README.md)
+        bool direct = false, covered = true;
+        for (auto& sp : c->plan.segs) direct |= (sp.nt == 0 && sp.d.out_len > 0);
+        int cur = 0;
+        for (auto& rg : c->plan.out_ranges) { if (rg.first > cur) covered = false; cur = std::max(cur, rg.second); }
+        if (cur < R) covered = false;
+        if (!direct && covered) {
+            MtdPlan* mp = nullptr;
+            int rc = get_mtd_plan(c, P, k.kaiser_beta, &mp);
+            if (rc) return rc;
+            int zlo, zhi;
+            if (zero_v_rows(P, k.zero_v_div, &zlo, &zhi)) return fail(c, RB200_ERR_INDEX, "fun_0v_pressing: Index in position 1 is invalid");
+            const int ring_slots = 3;
+            rb200_ctx::Slot& sl = c->slots[0];
+            CK(c, c->ring.ensure((size_t)ring_slots * cpi_cells * sizeof(float2)));
+            CK(c, c->colmask.ensure((size_t)n_cpi * C * R * sizeof(unsigned long long)));
+            CK(c, sl.vlist.ensure((size_t)k.max_det * sizeof(rb200_det)));
+            CK(c, c->megactr.ensure((size_t)(1 + 2 * n_cpi) * sizeof(int)));
+            Chain64Params q;
+            memset(&q, 0, sizeof q);
+            q.pc.in = raw_dev;
+            q.pc.hperm = c->plan.hperm.as<float2>();
+            q.pc.tw = c->plan.classes[0].tw.as<float2>();
+            q.pc.tiles = c->plan.classes[0].tiles.as<int2>();
+            q.pc.gain = c->gain_n ? c->gain.as<float>() : nullptr;
+            for (size_t i = 0; i < c->plan.segs.size(); ++i) q.pc.segs[i] = c->plan.segs[i].d;
+            q.pc.R = R; q.pc.R_out = R; q.pc.C = C; q.pc.P = P;
+            for (int i = 0; i < 64; ++i) {
+                q.m.win[i] = mp->h_window[i];
+                q.m.keep[i] = (i >= zlo && i <= zhi) ? 0.f : 1.f;
+            }
+            q.m.out = rdm_dev;
+            q.m.in_ld = q.m.out_ld = q.m.cols = R;
+            q.m.meth_v = k.cfar_method_v;
+            q.m.tv_over_ref = (float)(k.cfar_t_v / k.cfar_ref_v);
+            q.m.dets = sl.vlist.p;
+            q.m.det_count = sl.count.as<int>();
+            q.m.colmask = c->colmask.as<unsigned long long>();
+            q.m.cols_ld = R;
+            q.m.max_det = k.max_det;
+            q.m.n_lanes = C;
+            q.m.cpi0 = 0;
+            q.n_cpi = n_cpi;
+            q.n_tiles = c->plan.classes[0].n_tiles;
+            q.n_pc_items = P * q.n_tiles;
+            q.n_mtd_items = C * ((R + 255) / 256);
+            q.ring = c->ring.as<float2>();
+            q.ring_slots = ring_slots;
+            q.ring_stride = cpi_cells;
+            q.work_counter = c->megactr.as<int>();
+            q.pc_done = c->megactr.as<int>() + 1;
+            q.mtd_done = c->megactr.as<int>() + 1 + n_cpi;
+            q.err_flag = c->errflag.as<int>();
+            CK(c, cudaMemsetAsync(c->megactr.p, 0, (size_t)(1 + 2 * n_cpi) * sizeof(int), st));
+            CK(c, cudaEventRecord(c->ev0, st));
+            const bool timed = c->stage_timing && c->stage_used + 4 <= 65536;
+            if (timed) { stage_event(c, st); c->stage_cpis.push_back(n_cpi); }
+            CK(c, launch_chain64(q, c->n_sms, st));
+            c->launches++;
+            if (timed) { stage_event(c, st); stage_event(c, st); }
+            cp.cpi0 = 0;
+            CK(c, launch_cfar_r64(rdm_dev, cp, (float)k.cfar_t_r, sl.vlist.p, sl.count.as<int>(), c->dets_v.p, c->dets_2d.p,
+                                  c->counters.as<int>(), c->colmask.as<unsigned long long>(), R, c->errflag.as<int>(), c->n_sms * 2, st));
+            c->launches++;
+            if (timed) stage_event(c, st);
+            CK(c, cudaEventRecord(c->ev1, st));
+            c->have_timing = true;
+            c->last_chunk_cpis = 0;
+            c->last_pc = nullptr;
+            c->last_was_mega = true;
+            return RB200_OK;
+        }
+    }
     if (fused) {
         MtdPlan* mp = nullptr;
         int rc = get_mtd_plan(c, P, k.kaiser_beta, &mp);
@@ -1093,6 +1176,7 @@ static int chain_fetch(rb200_ctx* c, rb200_det* dets, bool dets_on_device, int* 
     CK(c, cudaStreamSynchronize(st));
     const int nv = c->h_counts[0], n2 = c->cfg.cfar_range_stage ? c->h_counts[1] : 0;
     if (n_det) *n_det = nv + n2;
+    if (c->h_counts[3] == 2) return fail(c, RB200_ERR_CUDA, "fused chain kernel: a dependency wait timed out (internal error)");
     if (c->h_counts[3]) return fail(c, RB200_ERR_INDEX, "executeCFAR: Index exceeds array bounds (CFAR axis shorter than 2*(ref+guard))");
     if (dets) {
         // 2-D records first (the product), then velocity-stage records; at most max_det in total
@@ -1131,7 +1215,7 @@ extern "C" int rb200_debug_fetch_pc(rb200_ctx* c, int cpi_in_chunk, float* out_r
     if (!c || !out_ri || cpi_in_chunk < 0 || cpi_in_chunk >= c->last_chunk_cpis) return fail(c, RB200_ERR_ARG, "debug_fetch_pc: bad argument");
     cudaSetDevice(c->device);
     const size_t cpi_cells = (size_t)c->cfg.n_prt * c->cfg.n_range * c->cfg.n_lanes;
-    if (!c->last_pc) return fail(c, RB200_ERR_ARG, "debug_fetch_pc: no chain call yet");
+    if (!c->last_pc) return fail(c, RB200_ERR_ARG, "debug_fetch_pc: no chunked chain call yet (set RB200_NO_MEGA=1 to keep the intermediate)");
     CK(c, cudaDeviceSynchronize());
     CK(c, cudaMemcpy(out_ri, c->last_pc + (size_t)cpi_in_chunk * cpi_cells, cpi_cells * sizeof(float2), cudaMemcpyDeviceToHost));
     return RB200_OK;

@@ -82,6 +82,23 @@ struct Mtd64Params {
     int max_det, n_lanes, cpi0;
 };
 
+// fused persistent chain for P = 64, 16 channels (chain64_kernel.cu)
+struct Chain64Params {
+    PcParams pc;            // in = raw wire samples of the whole batch; out unused (ring below); R, R_out, segs, hperm, tw, tiles, gain
+    Mtd64Params m;          // out = RDM of the whole batch, dets / det_count / colmask for the whole batch, cpi0 = 0
+    int n_cpi;
+    int n_tiles;            // overlap-save tiles per PRT line group
+    int n_pc_items;         // per CPI: 64 * n_tiles
+    int n_mtd_items;        // per CPI: 16 * ceil(R / 256)
+    float2* ring;           // pulse-compressed intermediate, ring_slots CPIs of [lane][prt][range]
+    int ring_slots;
+    size_t ring_stride;     // float2 elements per CPI slot
+    int* work_counter;      // zeroed before launch
+    int* pc_done;           // [n_cpi], zeroed before launch
+    int* mtd_done;          // [n_cpi], zeroed before launch
+    int* err_flag;
+};
+
 struct CfarParams {
     int V, R;               // full RDM size
     int v_lo, v_hi;         // 0-based tested rows [v_lo, v_hi)  (n0+1 .. V-n0)

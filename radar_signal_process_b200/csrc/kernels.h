@@ -12,7 +12,8 @@ int pc_tile_lanes(int nt, bool wire);
 void pc_build_twiddles(int nt, std::vector<float2>& tw);   // stage-major twiddle table for tile size nt     // lines per CTA for FFT tile size nt (0 = unsupported)
 cudaError_t launch_pc_fft(int nt, bool wire, const PcParams& p, int n_tiles, int n_groups, cudaStream_t st);
 // persistent TMA-prefetch variant: wire format, 16 channels, 256-sample tiles
-cudaError_t launch_pc_fft_tma(const PcParams& p, int n_tiles, int n_groups, int n_sms, int ctas_per_sm, cudaStream_t st);
+// h_entries: float2 entries of PcParams::hperm to keep resident in shared memory (all segment spectra)
+cudaError_t launch_pc_fft_tma(const PcParams& p, int n_tiles, int n_groups, int n_sms, int ctas_per_sm, int h_entries, cudaStream_t st);
 cudaError_t launch_pc_direct(bool wire, const PcParams& p, const float2* taps, int seg_idx, int out_len, int n_lines, cudaStream_t st);
 cudaError_t launch_pc_zero_cols(float2* out, size_t n_lines, int R, int c0, int c1, cudaStream_t st);
 cudaError_t launch_unpack(const int16_t* raw, float2* out, int n_groups, int P, int R, int C, cudaStream_t st);
@@ -29,6 +30,9 @@ cudaError_t launch_mtd64_tma(const Mtd64Params& p, int n_slabs, int n_sms, int c
 cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, const void* slot_v, int* slot_count, void* dets_v,
                             void* dets_2d, int* gcount, const unsigned long long* colmask, int cols_ld, int* err_flag, int n_blocks,
                             cudaStream_t st);
+
+// ---- fused persistent PC + MTD64 + velocity CFAR for a whole batch (chain64_kernel.cu)
+cudaError_t launch_chain64(const Chain64Params& q, int n_sms, cudaStream_t st);
 
 // ---- K3 CFAR (cfar_kernels.cu)
 // chain variant: float RDM [slab][V][R] row-major -> velocity-hit list + 2-D list (+ optional dense uint8 flags)

@@ -23,129 +23,13 @@
 // contiguous bytes of one output line.
 #include "common.cuh"
 #include "radix.cuh"
+#include "pc_core.cuh"
 #include "kernels.h"
 #include <algorithm>
 #include <cmath>
 #include <vector>
 
 namespace rb {
-
-// offset (in float2) of the stage-s twiddle block inside PcParams::tw:  T_s[k*st_s + q] = w_NT^(q*k*R^s),
-// st_s = NT / R^(s+1).  Blocks exist for s = 0 .. S-2 (the last stage has no twiddles).
-template <int R, int S> __host__ __device__ constexpr int tw_block_off(int s) {
-    int off = 0;
-    for (int i = 0; i < s; ++i) off += R * (ipow(R, S) / ipow(R, i + 1));
-    return off;
-}
-
-template <int R, int S, int LT> struct PcOcc { static constexpr int min_blocks = (LT * (ipow(R, S) / R) <= 256) ? 3 : 1; };
-
-// One forward DIF stage s >= 1: exchange through shared memory (write at the positions of stage s-1, read at
-// the positions of stage s), butterfly, twiddle.  All strides are template constants.
-template <int R, int S, int s>
-__device__ __forceinline__ void pc_fwd_stage(float2 (&v)[R], float2* line_sm, const float2* __restrict__ twtab, int u) {
-    constexpr int NT = ipow(R, S);
-    constexpr int sp = NT / ipow(R, s);            // stride of stage s-1
-    constexpr int st = NT / ipow(R, s + 1);        // stride of stage s
-    constexpr int twoff = tw_block_off<R, S>(s);
-    const int basep = (u / sp) * sp * R + (u % sp);
-#pragma unroll
-    for (int k = 0; k < R; ++k) line_sm[basep + k * sp] = v[k];
-    __syncthreads();
-    const int q = u % st;
-    const int base = (u / st) * st * R + q;
-#pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = line_sm[base + j * st];
-    Dft<R, -1>::run(v);
-    if (st > 1) {
-        const float2* tw = twtab + twoff + q;
-#pragma unroll
-        for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(tw + k * st));
-    }
-}
-
-// One inverse DIT stage s >= 1: conjugate twiddle, butterfly, exchange towards stage s-1.  When s-1 == 0 the
-// read side is re-mapped butterfly-fastest (out_lane, out_u) so the final stores coalesce along range.
-template <int R, int S, int s, int LT>
-__device__ __forceinline__ void pc_inv_stage(float2 (&v)[R], float2* sm, const float2* __restrict__ twtab, int t, int lane, int u,
-                                             int& out_lane, int& out_u) {
-    constexpr int NT = ipow(R, S);
-    constexpr int NB = NT / R;
-    constexpr int LS = NT + 1;
-    constexpr int st = NT / ipow(R, s + 1);
-    constexpr int sn = NT / ipow(R, s);            // stride of stage s-1
-    constexpr int twoff = tw_block_off<R, S>(s);
-    float2* line_sm = sm + lane * LS;
-    const int q = u % st;
-    if (st > 1) {
-        const float2* tw = twtab + twoff + q;
-#pragma unroll
-        for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], __ldg(tw + k * st));
-    }
-    Dft<R, +1>::run(v);
-    const int base = (u / st) * st * R + q;
-#pragma unroll
-    for (int j = 0; j < R; ++j) line_sm[base + j * st] = v[j];
-    __syncthreads();
-    if (s - 1 == 0) {
-        out_lane = t / NB;
-        out_u = t % NB;
-        const float2* src = sm + out_lane * LS + out_u;
-#pragma unroll
-        for (int k = 0; k < R; ++k) v[k] = src[k * sn];
-    } else {
-        const int basen = (u / sn) * sn * R + (u % sn);
-#pragma unroll
-        for (int k = 0; k < R; ++k) v[k] = line_sm[basen + k * sn];
-    }
-}
-
-// Forward DIF -> spectrum multiply -> inverse DIT on the R operands of one thread (see file header).
-// On return v[j] holds lag out_u + j*NB of line out_lane (butterfly-fastest mapping for coalesced stores).
-template <int R, int S, int LT>
-__device__ __forceinline__ void pc_fft_core(float2 (&v)[R], float2* sm, const PcParams& p, const PcSegDev& sg,
-                                            int t, int lane, int u, int& out_lane_r, int& out_u_r) {
-    static_assert(S >= 1 && S <= 3, "1..3 stages");
-    constexpr int NT = ipow(R, S);
-    constexpr int NB = NT / R;
-    constexpr int LS = NT + 1;
-    float2* line_sm = sm + lane * LS;
-
-    // ---- forward DIF ----
-    Dft<R, -1>::run(v);
-    if (S > 1) {
-        const float2* tw = p.tw + u;      // stage-0 block: T[k*NB + u]
-#pragma unroll
-        for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(tw + k * NB));
-    }
-    if (S >= 2) pc_fwd_stage<R, S, 1>(v, line_sm, p.tw, u);
-    if (S >= 3) pc_fwd_stage<R, S, (S >= 3 ? 2 : 1)>(v, line_sm, p.tw, u);
-
-    // ---- reference spectrum (digit-reversed order == this thread's positions u*R .. u*R+R-1) ----
-    {
-        const float4* hp = reinterpret_cast<const float4*>(p.hperm + sg.h_off + u * R);
-#pragma unroll
-        for (int k = 0; k < R; k += 2) {
-            const float4 h = __ldg(hp + k / 2);
-            v[k] = cmul(v[k], make_float2(h.x, h.y));
-            v[k + 1] = cmul(v[k + 1], make_float2(h.z, h.w));
-        }
-    }
-
-    // ---- inverse DIT ----
-    int out_lane = lane, out_u = u;
-    if (S >= 3) pc_inv_stage<R, S, (S >= 3 ? 2 : 1), LT>(v, sm, p.tw, t, lane, u, out_lane, out_u);
-    if (S >= 2) pc_inv_stage<R, S, 1, LT>(v, sm, p.tw, t, lane, u, out_lane, out_u);
-    if (S > 1) {
-        // stage 0 (operands fetched with the store mapping)
-        const float2* tw = p.tw + out_u;
-#pragma unroll
-        for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], __ldg(tw + k * NB));
-    }
-    Dft<R, +1>::run(v);
-    out_lane_r = out_lane;
-    out_u_r = out_u;
-}
 
 template <int R, int S, int LT, bool WIRE, int CFIX>
 __global__ void __launch_bounds__(LT * (ipow(R, S) / R), PcOcc<R, S, LT>::min_blocks)
@@ -223,7 +107,7 @@ pc_fft_kernel(const PcParams p) {
         }
     }
     int out_lane, out_u;
-    pc_fft_core<R, S, LT>(v, sm, p, sg, t, lane, u, out_lane, out_u);
+    pc_fft_core<R, S, LT, false>(v, sm, p.tw, p.hperm + sg.h_off, t, lane, u, out_lane, out_u);
 
     // ---- store the alias-free lags ----
     {
@@ -271,39 +155,9 @@ pc_fft_kernel(const PcParams p) {
 // the CTA is still transforming the previous item, so the global-load latency never stalls the
 // butterflies.  Grid = resident CTAs (SMs x 3); items (line group, tile) are taken round-robin.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
 template <int R, int S>
 __global__ void __launch_bounds__(16 * (ipow(R, S) / R), PcOcc<R, S, 16>::min_blocks)
-pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles) {
+pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
     constexpr int LT = 16;
     constexpr int NT = ipow(R, S);
     constexpr int NB = NT / R;
@@ -313,6 +167,10 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
     int* rawbuf = reinterpret_cast<int*>(smem_raw + FFT_BYTES);
+    // resident tables: stage-major twiddles and up to TAB_SEGS segment spectra (each NT float2)
+    constexpr int TW_N = tw_block_off<R, S>(S - 1) > 0 ? tw_block_off<R, S>(S - 1) : 1;
+    float2* tw_sm = reinterpret_cast<float2*>(smem_raw + FFT_BYTES + 2 * RAW_INTS * 4);
+    float2* h_sm = tw_sm + TW_N;
     __shared__ __align__(8) uint64_t mbar[2];
 
     const int t = threadIdx.x;
@@ -323,6 +181,8 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles) {
         mbar_init(&mbar[1], 1);
         mbar_fence_init();
     }
+    for (int i = t; i < TW_N; i += blockDim.x) tw_sm[i] = __ldg(p.tw + i);
+    for (int i = t; i < h_entries; i += blockDim.x) h_sm[i] = __ldg(p.hperm + i);
     __syncthreads();
 
     // thread 0: start the bulk copy of an item's valid input span into staging buffer `buf`
@@ -388,7 +248,7 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles) {
             if (t == 0 && next < n_items) issue(next, buf ^ 1);
         }
         int out_lane, out_u;
-        pc_fft_core<R, S, LT>(v, sm, p, sg, t, lane, u, out_lane, out_u);
+        pc_fft_core<R, S, LT, true>(v, sm, tw_sm, h_sm + sg.h_off, t, lane, u, out_lane, out_u);
         {
             const int cpi = g / p.P, prt = g - cpi * p.P;
             const size_t oline = ((size_t)cpi * LT + out_lane) * p.P + prt;
@@ -520,10 +380,10 @@ void pc_build_twiddles(int nt, std::vector<float2>& tw) {
     if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
 }
 
-cudaError_t launch_pc_fft_tma(const PcParams& p, int n_tiles, int n_groups, int n_sms, int ctas_per_sm, cudaStream_t st) {
+cudaError_t launch_pc_fft_tma(const PcParams& p, int n_tiles, int n_groups, int n_sms, int ctas_per_sm, int h_entries, cudaStream_t st) {
     constexpr int R = 16, S = 2, NT = 256, LT = 16;
     const size_t fft_bytes = ((size_t)LT * (NT + 1) * sizeof(float2) + 127) / 128 * 128;
-    const size_t smem = fft_bytes + 2 * (size_t)NT * LT * 4;
+    const size_t smem = fft_bytes + 2 * (size_t)NT * LT * 4 + ((size_t)tw_block_off<R, S>(S - 1) + h_entries) * sizeof(float2);
     static size_t configured[64] = {};
     cudaError_t ce = ensure_dynamic_smem(pc_fft_tma_kernel<R, S>, smem, configured);
     if (ce != cudaSuccess) return ce;
@@ -531,7 +391,7 @@ cudaError_t launch_pc_fft_tma(const PcParams& p, int n_tiles, int n_groups, int 
     if (n_items <= 0 || n_items > 0x7fffffffLL) return n_items <= 0 ? cudaSuccess : cudaErrorInvalidConfiguration;
     const int per_sm = std::max(1, std::min(ctas_per_sm, (int)PcOcc<R, S, LT>::min_blocks));
     const int grid = (int)std::min<long long>(n_items, (long long)n_sms * per_sm);
-    pc_fft_tma_kernel<R, S><<<grid, LT * (NT / R), smem, st>>>(p, (int)n_items, n_tiles);
+    pc_fft_tma_kernel<R, S><<<grid, LT * (NT / R), smem, st>>>(p, (int)n_items, n_tiles, h_entries);
     return cudaGetLastError();
 }
 
