@@ -33,6 +33,7 @@ P, R, C = 64, 4096, 16
 CELLS = P * R * C
 ALG_BYTES_PER_CPI = CELLS * 8          # 4 B int16 I/Q read + 4 B fp32 RDM magnitude written per cell
 CFAR = (5, 7, 5.0, 0, 5, 7, 5.0, 0, 0, 1)
+K1_DRAM_BYTES_PER_CPI = (134.603008e6 + 212.313344e6) / 8.0     # ncu, cold cache, see profiles/r01d_ncu_full_chunk8.txt
 METRIC = "CPI frames/s (PC->MTD->0v->CFAR, 64 PRT x 4096 range x 16 lanes int16 DDC)"
 
 
@@ -101,6 +102,25 @@ def cpu_reference_rate(n_cpis, first_cpi=0, workers=None):
         vec.chain(raw[i:i + 1], 1, P, R, C, ("single", waveforms.REF_DDC), CFAR)
     dt = time.perf_counter() - t0
     return n_cpis / dt, dt
+
+
+def cpu_loop_faithful_rate():
+    """The loop-faithful transcription (oracle/mcode.py: per-PRT pulse-compression loop with fft(h) recomputed per
+    PRT, per-range-cell Doppler loop, per-hit range-CFAR loop; one thread, like a MATLAB script) on ONE lane of one
+    S3 CPI, extrapolated x16 lanes.  Returns (cpis_per_s, seconds measured)."""
+    from oracle import mcode
+    from radar_signal_process_b200 import waveforms, workload
+    raw = workload.synth_batch(1)
+    x = raw[0, :, :, 0, 0].astype(np.float64) + 1j * raw[0, :, :, 0, 1].astype(np.float64)      # lane 0: P x R
+    t0 = time.perf_counter()
+    pc = np.zeros(x.shape, dtype=np.complex128)
+    L = waveforms.REF_DDC.size
+    for i in range(P):                                                   # MTD/fun_lss_pulse_compression.m:36,42,63-65
+        pc[i, :] = mcode.fun_pulse_compression(waveforms.REF_DDC, x[i, :])[L - 1:L - 1 + R]
+    rdm = mcode.fun_0v_pressing(mcode.fun_Process_MTD(pc, R, P), 150)
+    mcode.executeCFAR(rdm, *CFAR)
+    dt = time.perf_counter() - t0
+    return 1.0 / (dt * C), dt
 
 
 def run_reference(args):
@@ -273,9 +293,12 @@ def run_gpu(args):
                        "parallelism": "cpi-shard x%d, no hot-path collective" % world},
             "hbm_gbs_chain": value / world * ALG_BYTES_PER_CPI / 1e9,
             "hbm_frac_chain": value / world * ALG_BYTES_PER_CPI / 1e9 / peak,
-            "roofline": {"bound": "hbm", "kernel": "pc_fft_kernel (K1: unpack + pulse compression)",
+            "roofline": {"bound": "hbm", "kernel": "pc_fft_tma_kernel (K1: int16 unpack + overlap-save pulse compression; 60 % of the chain's device time)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": None, "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the ncu --set full
+                         # capture profiles/r01d_ncu_full_chunk8.txt (134.6 MB read + 212.3 MB written per 8-CPI launch)
+                         "traffic": K1_DRAM_BYTES_PER_CPI * cpis_per_launch, "traffic_source": "profiles/r01d_ncu_full_chunk8.txt",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_CPI * cpis_per_launch,
                          "ms_per_launch": pc_ms_per_launch,
                          "serialised_ms_per_step": ms_serial / args.steps,
@@ -289,8 +312,11 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             cps, dt = cpu_reference_rate(args.cpu_cpis)
+            loop_cps, loop_dt = cpu_loop_faithful_rate()
             line["cpu_baseline"] = {"value": cps, "unit": "CPI/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "%d CPIs of the S3 workload through oracle/vec.py (float64, scipy.fft workers=all), %.1f s" % (args.cpu_cpis, dt)}
+                                    "sample": "%d CPIs of the S3 workload through oracle/vec.py (float64, scipy.fft workers=all), %.1f s" % (args.cpu_cpis, dt),
+                                    "loop_faithful": {"value": loop_cps, "unit": "CPI/s", "cores": 1,
+                                                      "sample": "oracle/mcode.py (M-code loop structure) on 1 of 16 lanes of one CPI, %.1f s, extrapolated x16" % loop_dt}}
         print(json.dumps(line))
     ctx.close()
     if world > 1:
