@@ -167,6 +167,7 @@ struct rb200_ctx {
     Slot slots[kMaxSlots];
     cudaEvent_t fork_ev = nullptr;
     const float2* last_pc = nullptr;
+    cudaStream_t last_stream = nullptr;   // stream of the last chain_enqueue: rb200_chain_fetch orders itself after it
     // MATLAB-layout scratch
     DevBuf s_in_re, s_in_im, s_a, s_b, s_c, s_out_re, s_out_im, s_u8a, s_u8b, s_idx;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1166,7 +1167,8 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
 extern "C" int rb200_chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float* rdm_dev, void* stream) {
     if (!c || !raw_dev) return fail(c, RB200_ERR_ARG, "chain_enqueue: bad argument");
     cudaSetDevice(c->device);
-    return chain_enqueue(c, raw_dev, n_cpi, rdm_dev, stream ? (cudaStream_t)stream : c->stream);
+    c->last_stream = stream ? (cudaStream_t)stream : c->stream;
+    return chain_enqueue(c, raw_dev, n_cpi, rdm_dev, c->last_stream);
 }
 
 static int chain_fetch(rb200_ctx* c, rb200_det* dets, bool dets_on_device, int* n_det, cudaStream_t st) {
@@ -1194,7 +1196,8 @@ static int chain_fetch(rb200_ctx* c, rb200_det* dets, bool dets_on_device, int* 
 extern "C" int rb200_chain_fetch(rb200_ctx* c, rb200_det* dets_host, int* n_det) {
     if (!c) return RB200_ERR_ARG;
     cudaSetDevice(c->device);
-    return chain_fetch(c, dets_host, dets_host && is_device_ptr(dets_host), n_det, c->stream);
+    // same stream as the enqueue: the copies are ordered after the chain's kernels
+    return chain_fetch(c, dets_host, dets_host && is_device_ptr(dets_host), n_det, c->last_stream ? c->last_stream : c->stream);
 }
 
 extern "C" int rb200_chain_i16(rb200_ctx* c, const int16_t* raw, int n_cpi, float* rdm_out, rb200_det* dets, int* n_det, void* stream) {

@@ -177,6 +177,9 @@ chain64_kernel(const Chain64Params q) {
                     }
                 }
             }
+            // generic-proxy reads of the staging buffer are ordered before the TMA (async-proxy) refill that thread 0
+            // issues for a later item
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (t == 0) nxt = claim();            // prefetch: the other staging buffer was consumed one PC item ago
             int out_lane, out_u;
             pc_fft_core<R, S, LT, false>(v, sm, p.tw, p.hperm + sg.h_off, t, lane, u, out_lane, out_u);

@@ -59,17 +59,35 @@ __global__ void __launch_bounds__(128, RB200_MTD64_MINB)
 mtd64_tma_kernel(const Mtd64Params p, int tiles_per_slab, int n_items) {
     constexpr int P = 64;
     extern __shared__ __align__(128) float2 tile[];    // [64][128]
-    __shared__ __align__(8) uint64_t mbar;
+    // full : completes when the 64 row copies of an item have landed (TMA complete_tx)
+    // empty: completes when all 128 threads have pulled their column of the current item into registers; the
+    //        producers wait on it before overwriting the tile (generic-proxy reads -> async-proxy writes need a
+    //        real acquire: a bare bar.sync let a late warp observe rows of the next item)
+    __shared__ __align__(8) uint64_t full_bar, empty_bar;
     const int t = threadIdx.x;
     if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(m64_smem_u32(&mbar)), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(m64_smem_u32(&full_bar)), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(m64_smem_u32(&empty_bar)), "r"(128));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    auto wait_bar = [&](uint64_t* bar, uint32_t parity) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "LAB_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+            "@P1 bra DONE;\n"
+            "bra LAB_WAIT;\n"
+            "DONE:\n"
+            "}" ::"r"(m64_smem_u32(bar)),
+            "r"(parity)
+            : "memory");
+    };
     auto expect = [&](int item) {          // thread 0
         const int c0 = (item % tiles_per_slab) * 128;
         const uint32_t bytes = (uint32_t)min(128, p.cols - c0) * 8u * P;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m64_smem_u32(&mbar)), "r"(bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m64_smem_u32(&full_bar)), "r"(bytes) : "memory");
     };
     auto copy_row = [&](int item) {        // threads 0..63: one PRT row each
         const int slab = item / tiles_per_slab;
@@ -77,43 +95,35 @@ mtd64_tma_kernel(const Mtd64Params p, int tiles_per_slab, int n_items) {
         const uint32_t bytes = (uint32_t)min(128, p.cols - c0) * 8u;
         const float2* src = p.in + ((size_t)slab * P + t) * p.in_ld + c0;
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(m64_smem_u32(tile + t * 128)),
-                     "l"(src), "r"(bytes), "r"(m64_smem_u32(&mbar))
+                     "l"(src), "r"(bytes), "r"(m64_smem_u32(&full_bar))
                      : "memory");
     };
     int item = blockIdx.x;
     if (item < n_items) {
         if (t == 0) expect(item);
-        __syncthreads();
         if (t < P) copy_row(item);
     }
     for (int it = 0; item < n_items; item += gridDim.x, ++it) {
         const int slab = item / tiles_per_slab;
         const int r = (item - slab * tiles_per_slab) * 128 + t;
         const bool ok = r < p.cols;
-        {
-            const uint32_t parity = (uint32_t)(it & 1);
-            asm volatile(
-                "{\n"
-                ".reg .pred P1;\n"
-                "LAB_WAIT:\n"
-                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-                "@P1 bra DONE;\n"
-                "bra LAB_WAIT;\n"
-                "DONE:\n"
-                "}" ::"r"(m64_smem_u32(&mbar)),
-                "r"(parity)
-                : "memory");
-        }
+        wait_bar(&full_bar, (uint32_t)(it & 1));
         float2 v[P];
 #pragma unroll
         for (int prt = 0; prt < P; ++prt) {
             const float2 x = tile[prt * 128 + t];
             v[prt] = make_float2(x.x * p.win[prt], x.y * p.win[prt]);
         }
+        // this thread's column is in registers: order the generic-proxy reads above before the async-proxy (TMA) writes
+        // that the producers will issue once everybody has arrived, then release the tile
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(m64_smem_u32(&empty_bar)) : "memory");
         const int next = item + gridDim.x;
-        if (t == 0 && next < n_items) expect(next);
-        __syncthreads();                    // every thread has its column in registers: the tile buffer is free
-        if (next < n_items && t < P) copy_row(next);
+        if (next < n_items && t < P) {
+            if (t == 0) expect(next);
+            wait_bar(&empty_bar, (uint32_t)(it & 1));      // every thread of the CTA is done with the tile
+            copy_row(next);
+        }
         mtd64_column<REF, GUARD, N0, CFAR>(v, p, slab, r, ok);
     }
 }

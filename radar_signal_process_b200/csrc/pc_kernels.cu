@@ -242,6 +242,9 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
                 }
             }
         }
+        // generic-proxy reads of the staging buffer are ordered before the TMA (async-proxy) refill that thread 0
+        // issues for a later item
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         // the other staging buffer was consumed one iteration ago (every thread has passed a barrier since)
         {
             const int next = item + gridDim.x;

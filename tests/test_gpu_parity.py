@@ -449,3 +449,37 @@ def test_chain_device_resident_fused_persistent_kernel(lib):
     out = vec.chain(raw[:2], 2, P, R, C, ("single", ref), cfar, near_tol=RTOL)
     _close(rdm_m[:2], out["rdm"])
     _compare_flags(dets_m[dets_m["cpi"] < 2], out, 2, C, P, R, lib)
+
+
+def test_chain_is_deterministic_across_runs(lib):
+    """Repeated runs of the same device-resident batch (two chunks on two slot streams, TMA-staged kernels running
+    concurrently) give bit-identical RDMs and identical detection sets.  Regression test for a cross-proxy WAR race
+    (generic-proxy tile reads vs the TMA refill) that showed up as 32-column blocks of wrong RDM values."""
+    import torch
+    P, R, C, B = 64, 4096, 16, 16
+    raw = np.concatenate([synth.s3_batch(4)[0]] * 4, axis=0)
+    ref = mcode.load_ref("refDDCDataMF1")
+    dev = torch.device("cuda", 0)
+    raw_d = torch.from_numpy(raw).to(dev)
+    rdm_d = torch.zeros((B, C, P, R), dtype=torch.float32, device=dev)
+    stream = torch.cuda.Stream(dev)
+
+    def key(d):
+        return np.sort(d, order=["cpi", "lane", "v", "r", "kind"])
+
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), synth.cfar_tuple(synth.S3_CFAR), max_det=1 << 19,
+                    chunk_cpi=8) as ctx:
+        first = None
+        for it in range(25):
+            with torch.cuda.stream(stream):
+                rdm_d.zero_()
+                ctx.chain_enqueue(raw_d.data_ptr(), B, rdm_d.data_ptr(), stream.cuda_stream)
+                dets, n = ctx.chain_fetch()          # ordered after the enqueue on the same stream
+                stream.synchronize()
+            cur = (rdm_d.cpu().numpy(), key(dets))
+            if first is None:
+                first = cur
+                assert n > 0
+                continue
+            assert np.array_equal(cur[0], first[0]), "run %d: %d RDM cells differ" % (it, int((cur[0] != first[0]).sum()))
+            assert len(cur[1]) == len(first[1]) and all(np.array_equal(cur[1][f], first[1][f]) for f in cur[1].dtype.names)
