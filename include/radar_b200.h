@@ -211,9 +211,10 @@ int rb200_get_stage_ms(rb200_ctx* ctx, float ms[3], int* n_chunks, int* n_cpis);
 
 /* ---- "next" rows ---------------------------------------------------------*/
 
-/* f1: DBF weighting fused into the unpack: beams = sig_C * W.' (FrameDataRead_xzr.m:158).
- * w_re/w_im: n_beams x n_lanes column-major (DBF_coeffs_data_C); n_beams = 0 disables.  When
- * enabled the chain's lane count downstream of the unpack is n_beams.                             */
+/* f1: DBF weighting fused into the unpack: beams = sig_C * W.' (FrameDataRead_xzr.m:158, non-conjugate
+ * transpose).  w_re/w_im: n_beams x n_lanes column-major (DBF_coeffs_data_C, bin_to_mat_xzr.m:23-29);
+ * w_im may be NULL; n_beams = 0 disables.  When enabled, every lane index downstream of the unpack
+ * (rdm_out [cpi][beam][v][range], rb200_det.lane) is a beam index and buffers are sized with n_beams.   */
 int rb200_set_dbf(rb200_ctx* ctx, const double* w_re, const double* w_im, int n_beams);
 
 #ifdef __cplusplus

@@ -313,7 +313,12 @@ def cfar_flag_segments(mtd, cfar_args, segments=((1, 82), (83, 318), (319, 868))
 # ----------------------------------------------------------------------------------------------
 # whole chain on the int16 wire format (the benchmark workload)
 # ----------------------------------------------------------------------------------------------
-def chain(raw, n_cpi, P, R, C, plan, cfar, beta=8.0, zero_div=150, stc=None, mti_lag=0, near_tol=None):
+def dbf_weighting(x, W):
+    """``sig_C * W.'`` of FrameDataRead_xzr.m:158 on x[cpi, channel, prt, range] -> [cpi, beam, prt, range]."""
+    return np.einsum("bc,icpr->ibpr", np.asarray(W, dtype=np.complex128), x)
+
+
+def chain(raw, n_cpi, P, R, C, plan, cfar, beta=8.0, zero_div=150, stc=None, mti_lag=0, near_tol=None, dbf=None):
     """unpack -> [iSTC] -> PC -> [MTI] -> MTD -> 0-v -> executeCFAR for every (cpi, lane).
 
     ``plan`` is ("single", ref) | ("lss_mp", pulse2, pulse3) | ("lss_mtd", pulse2, pulse3, p1, p2, p3).
@@ -321,6 +326,8 @@ def chain(raw, n_cpi, P, R, C, plan, cfar, beta=8.0, zero_div=150, stc=None, mti
     Returns dict(rdm[cpi,lane,V,R], flag, flagV[, near, nearV]).
     """
     x = unpack_wire(raw, n_cpi, P, R, C)
+    if dbf is not None:
+        x = dbf_weighting(x, dbf)
     if stc is not None:
         x = istc(x, stc)
     if plan[0] == "single":

@@ -30,6 +30,7 @@ class Context:
             raise B.RadarB200Error(st, text.decode() if text else "")
         self._keep = None
         self.device = int(device)
+        self.n_out_lanes = self.cfg.n_lanes      # lanes downstream of the optional beam former
 
     # ---- lifetime -------------------------------------------------------------------------------
     def close(self):
@@ -69,6 +70,19 @@ class Context:
             return
         a = np.ascontiguousarray(stc_db, dtype=np.float64)
         self._ck(self._lib.rb200_set_stc(self._h, _fptr(a), a.size))
+
+    def set_dbf(self, W):
+        """DBF weighting fused into the unpack: beams = sig_C * W.' (FrameDataRead_xzr.m:158).
+        ``W``: (n_beams, n_lanes) complex (``DBF_coeffs_data_C``); ``None`` switches it off."""
+        if W is None:
+            self._ck(self._lib.rb200_set_dbf(self._h, None, None, 0))
+            self.n_out_lanes = self.cfg.n_lanes
+            return
+        W = np.asarray(W, dtype=np.complex128)
+        assert W.ndim == 2 and W.shape[1] == self.cfg.n_lanes, "W must be (n_beams, n_lanes)"
+        re, im = _split(W)
+        self._ck(self._lib.rb200_set_dbf(self._h, _fptr(re), _fptr(im), W.shape[0]))
+        self.n_out_lanes = W.shape[0]
 
     def set_cfar(self, refR, saveR, T_R, methR, refV, saveV, T_V, methV, n0, rflag):
         c = self.cfg
@@ -162,7 +176,7 @@ class Context:
         c = self.cfg
         raw = np.ascontiguousarray(raw, dtype=np.int16)
         assert raw.size == self._cells(n_cpi) * 2, "raw has the wrong number of samples for the configured geometry"
-        rdm = np.zeros((n_cpi, c.n_lanes, c.n_prt, c.n_range), dtype=np.float32) if want_rdm else None
+        rdm = np.zeros((n_cpi, self.n_out_lanes, c.n_prt, c.n_range), dtype=np.float32) if want_rdm else None
         dets = np.zeros(c.max_det, dtype=B.DET_DTYPE)
         n = C.c_int(0)
         st = self._lib.rb200_chain_i16(self._h, raw.ctypes.data, n_cpi, rdm.ctypes.data if want_rdm else None,
@@ -190,7 +204,7 @@ class Context:
 
     def debug_fetch_pc(self, cpi_in_chunk=0):
         c = self.cfg
-        out = np.zeros((c.n_lanes, c.n_prt, c.n_range), dtype=np.complex64)
+        out = np.zeros((self.n_out_lanes, c.n_prt, c.n_range), dtype=np.complex64)
         self._ck(self._lib.rb200_debug_fetch_pc(self._h, int(cpi_in_chunk), out.ctypes.data))
         return out
 

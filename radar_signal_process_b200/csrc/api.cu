@@ -150,6 +150,8 @@ struct rb200_ctx {
     int gain_n = 0;
     // chain buffers
     DevBuf raw, pc, rdm, dets_v, dets_2d, counters, vmask, errflag, colmask;
+    DevBuf dbf_w;                  // DBF weights float2 [beam][channel]; dbf_beams = 0 when off
+    int dbf_beams = 0;
     DevBuf ring, megactr;          // fused persistent chain: L2-resident PC ring, work / completion counters
     bool last_was_mega = false;
     int n_sms = 148;
@@ -161,7 +163,7 @@ struct rb200_ctx {
     struct Slot {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
-        DevBuf pc, colmask, vlist, count, raw, rdm;
+        DevBuf pc, colmask, vlist, count, raw, rdm, beams;
     };
     static const int kMaxSlots = 4;
     Slot slots[kMaxSlots];
@@ -576,7 +578,7 @@ extern "C" int rb200_destroy(rb200_ctx* c) {
         kv.second->tw.release();
         delete kv.second;
     }
-    DevBuf* bufs[] = {&c->gain, &c->raw, &c->pc, &c->rdm, &c->dets_v, &c->dets_2d, &c->counters, &c->vmask, &c->errflag, &c->colmask, &c->ring, &c->megactr,
+    DevBuf* bufs[] = {&c->gain, &c->raw, &c->pc, &c->rdm, &c->dets_v, &c->dets_2d, &c->counters, &c->vmask, &c->errflag, &c->colmask, &c->ring, &c->megactr, &c->dbf_w,
                       &c->s_in_re, &c->s_in_im, &c->s_a, &c->s_b, &c->s_c, &c->s_out_re, &c->s_out_im, &c->s_u8a, &c->s_u8b, &c->s_idx};
     for (DevBuf* b : bufs) b->release();
     if (c->h_dets) cudaFreeHost(c->h_dets);
@@ -584,7 +586,7 @@ extern "C" int rb200_destroy(rb200_ctx* c) {
     for (int i = 0; i < rb200_ctx::kMaxSlots; ++i) {
         rb200_ctx::Slot& sl = c->slots[i];
         if (sl.stream) cudaStreamSynchronize(sl.stream);
-        sl.pc.release(); sl.colmask.release(); sl.vlist.release(); sl.count.release(); sl.raw.release(); sl.rdm.release();
+        sl.pc.release(); sl.colmask.release(); sl.vlist.release(); sl.count.release(); sl.raw.release(); sl.rdm.release(); sl.beams.release();
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
@@ -639,10 +641,23 @@ extern "C" int rb200_set_stc(rb200_ctx* c, const double* stc_db, int n) {
 }
 
 extern "C" int rb200_set_dbf(rb200_ctx* c, const double* w_re, const double* w_im, int n_beams) {
-    if (!c) return RB200_ERR_ARG;
-    if (n_beams == 0) return RB200_OK;
-    (void)w_re; (void)w_im;
-    return fail(c, RB200_ERR_UNSUPPORTED, "rb200_set_dbf: DBF weighting (SURVEY 8f row f1) is not implemented in this build");
+    if (!c || n_beams < 0 || n_beams > 255 || (n_beams > 0 && !w_re)) return fail(c, RB200_ERR_ARG, "set_dbf: bad argument");
+    cudaSetDevice(c->device);
+    if (n_beams == 0) { c->dbf_beams = 0; return RB200_OK; }
+    const int nch = c->cfg.n_lanes;
+    if ((size_t)n_beams * nch * sizeof(float2) > 48 * 1024) return fail(c, RB200_ERR_UNSUPPORTED, "set_dbf: weight matrix larger than 48 KB");
+    // DBF_coeffs_data_C is n_beams x n_channels, column-major; device copy is [beam][channel]
+    std::vector<float2> w((size_t)n_beams * nch);
+    for (int b = 0; b < n_beams; ++b)
+        for (int ch = 0; ch < nch; ++ch) {
+            const size_t k = (size_t)b + (size_t)n_beams * ch;
+            w[(size_t)b * nch + ch] = make_float2((float)w_re[k], w_im ? (float)w_im[k] : 0.f);
+        }
+    CK(c, c->dbf_w.ensure(w.size() * sizeof(float2)));
+    CK(c, cudaMemcpyAsync(c->dbf_w.p, w.data(), w.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->dbf_beams = n_beams;
+    return RB200_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -954,11 +969,14 @@ static int chunk_size(const rb200_ctx* c) {
 static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float* rdm_dev, cudaStream_t st,
                          const int16_t* raw_host = nullptr, float* rdm_host = nullptr) {
     const rb200_config& k = c->cfg;
-    const int P = k.n_prt, R = k.n_range, C = k.n_lanes;
+    const int P = k.n_prt, R = k.n_range;
+    const int Cin = k.n_lanes;                                   // channels interleaved in the wire format
+    const int C = c->dbf_beams ? c->dbf_beams : Cin;             // lanes downstream of the (optional) beam former
     if (n_cpi < 1 || n_cpi > k.max_cpi) return fail(c, RB200_ERR_ARG, "chain: n_cpi must be in 1..max_cpi");
     if (k.cfar_n0 < 0) return fail(c, RB200_ERR_INDEX, "executeCFAR: Index in position 1 exceeds array bounds (MTD_0_num < 0)");
     const int G = chunk_size(c);
     const size_t cpi_cells = (size_t)P * R * C;
+    const size_t raw_cells = (size_t)P * R * Cin;
     const int Rw = (R + 31) / 32;
     CK(c, c->dets_v.ensure((size_t)k.max_det * sizeof(rb200_det)));
     CK(c, c->dets_2d.ensure((size_t)k.max_det * sizeof(rb200_det)));
@@ -986,7 +1004,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     c->last_was_mega = false;
     // ---- fused persistent kernel for the whole batch (chain64_kernel.cu): device-resident input and output, 16 channels,
     //      one 256-sample tile class covering the whole PRT
-    if (fused && raw_dev && rdm_dev && !raw_host && !rdm_host && C == 16 && c->plan.valid && c->plan.classes.size() == 1 &&
+    if (fused && raw_dev && rdm_dev && !raw_host && !rdm_host && C == 16 && !c->dbf_beams && c->plan.valid && c->plan.classes.size() == 1 &&
         c->plan.classes[0].nt == 256 && c->plan.max_in_end <= R && c->plan.max_out_end <= R && (reinterpret_cast<uintptr_t>(raw_dev) & 15) == 0 &&
         getenv("RB200_MEGA")) {      // opt-in: measured slower than the slot pipeline on B200 (profiles/README.md)
         bool direct = false, covered = true;
@@ -1093,7 +1111,8 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         CK(c, c->vmask.ensure((size_t)G * C * P * Rw * sizeof(uint32_t)));
     }
     for (int i = 0; i < n_slots; ++i) {
-        if (raw_host) CK(c, c->slots[i].raw.ensure((size_t)G * cpi_cells * 4));
+        if (raw_host) CK(c, c->slots[i].raw.ensure((size_t)G * raw_cells * 4));
+        if (c->dbf_beams) CK(c, c->slots[i].beams.ensure((size_t)G * cpi_cells * sizeof(float2)));
         if (rdm_host) CK(c, c->slots[i].rdm.ensure((size_t)G * cpi_cells * sizeof(float)));
     }
     CK(c, cudaEventRecord(c->ev0, st));
@@ -1106,16 +1125,24 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         const int g = std::min(G, n_cpi - c0);
         rb200_ctx::Slot& sl = c->slots[chunk_idx % n_slots];
         cudaStream_t cs = (fused && n_slots > 1) ? sl.stream : st;
-        const int16_t* raw_chunk = raw_dev ? raw_dev + (size_t)c0 * cpi_cells * 2 : nullptr;
+        const int16_t* raw_chunk = raw_dev ? raw_dev + (size_t)c0 * raw_cells * 2 : nullptr;
         if (raw_host) {
-            CK(c, cudaMemcpyAsync(sl.raw.p, raw_host + (size_t)c0 * cpi_cells * 2, (size_t)g * cpi_cells * 4, cudaMemcpyHostToDevice, cs));
+            CK(c, cudaMemcpyAsync(sl.raw.p, raw_host + (size_t)c0 * raw_cells * 2, (size_t)g * raw_cells * 4, cudaMemcpyHostToDevice, cs));
             raw_chunk = sl.raw.as<int16_t>();
         }
         float* rdm_chunk = rdm_host ? sl.rdm.as<float>() : (rdm_dev ? rdm_base + (size_t)c0 * cpi_cells : rdm_base);
         float2* pc_buf = fused ? sl.pc.as<float2>() : c->pc.as<float2>();
         const bool timed = c->stage_timing && c->stage_used + 4 <= 65536;
         if (timed) { stage_event(c, cs); c->stage_cpis.push_back(g); }
-        int rc = run_pc(c, c->plan, true, raw_chunk, pc_buf, R, R, C, P, g * P, 0, c->gain_n ? c->gain.as<float>() : nullptr, cs);
+        int rc;
+        if (c->dbf_beams) {
+            // f1: beams = sig_C * W.' fused with the unpack, then planar pulse compression over cpi x beam x PRT lines
+            CK(c, launch_dbf(raw_chunk, sl.beams.as<float2>(), c->dbf_w.as<float2>(), C, Cin, g * P, P, R, cs));
+            c->launches++;
+            rc = run_pc(c, c->plan, false, sl.beams.p, pc_buf, R, R, 1, P, 0, g * C * P, c->gain_n ? c->gain.as<float>() : nullptr, cs);
+        } else {
+            rc = run_pc(c, c->plan, true, raw_chunk, pc_buf, R, R, C, P, g * P, 0, c->gain_n ? c->gain.as<float>() : nullptr, cs);
+        }
         if (rc) return rc;
         if (timed) stage_event(c, cs);
         cp.cpi0 = c0;
@@ -1217,7 +1244,7 @@ extern "C" int rb200_chain_i16(rb200_ctx* c, const int16_t* raw, int n_cpi, floa
 extern "C" int rb200_debug_fetch_pc(rb200_ctx* c, int cpi_in_chunk, float* out_ri) {
     if (!c || !out_ri || cpi_in_chunk < 0 || cpi_in_chunk >= c->last_chunk_cpis) return fail(c, RB200_ERR_ARG, "debug_fetch_pc: bad argument");
     cudaSetDevice(c->device);
-    const size_t cpi_cells = (size_t)c->cfg.n_prt * c->cfg.n_range * c->cfg.n_lanes;
+    const size_t cpi_cells = (size_t)c->cfg.n_prt * c->cfg.n_range * (c->dbf_beams ? c->dbf_beams : c->cfg.n_lanes);
     if (!c->last_pc) return fail(c, RB200_ERR_ARG, "debug_fetch_pc: no chunked chain call yet (set RB200_NO_MEGA=1 to keep the intermediate)");
     CK(c, cudaDeviceSynchronize());
     CK(c, cudaMemcpy(out_ri, c->last_pc + (size_t)cpi_in_chunk * cpi_cells, cpi_cells * sizeof(float2), cudaMemcpyDeviceToHost));

@@ -18,6 +18,9 @@ cudaError_t launch_pc_direct(bool wire, const PcParams& p, const float2* taps, i
 cudaError_t launch_pc_zero_cols(float2* out, size_t n_lines, int R, int c0, int c1, cudaStream_t st);
 cudaError_t launch_unpack(const int16_t* raw, float2* out, int n_groups, int P, int R, int C, cudaStream_t st);
 
+// ---- DBF weighting fused with the unpack (dbf_kernel.cu): wire int16 -> float2 planar [cpi][beam][prt][range]
+cudaError_t launch_dbf(const int16_t* raw, float2* out, const float2* W, int n_beams, int n_ch, int n_groups, int P, int R, cudaStream_t st);
+
 // ---- K2 MTD (mtd_kernels.cu)
 bool mtd_has_fast_path(int P);
 cudaError_t launch_mtd(const MtdParams& p, int n_slabs, cudaStream_t st);

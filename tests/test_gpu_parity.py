@@ -483,3 +483,26 @@ def test_chain_is_deterministic_across_runs(lib):
                 continue
             assert np.array_equal(cur[0], first[0]), "run %d: %d RDM cells differ" % (it, int((cur[0] != first[0]).sum()))
             assert len(cur[1]) == len(first[1]) and all(np.array_equal(cur[1][f], first[1][f]) for f in cur[1].dtype.names)
+
+
+def test_chain_with_dbf_weighting(lib):
+    """16 DDC channels -> 13 beams (sig_C * W.') fused with the unpack, then the usual chain per beam."""
+    P, R, C, NB, B = 64, 1024, 16, 13, 2
+    rng = np.random.default_rng(31)
+    raw, _ = synth.s3_batch(B, P=P, R=R, C=C, n_targets=3, r_lo=50, r_hi=R - 100)
+    W = (rng.normal(size=(NB, C)) + 1j * rng.normal(size=(NB, C))) / 4.0
+    ref = mcode.load_ref("refDDCDataMF1")
+    cfar = synth.cfar_tuple(synth.S3_CFAR)
+    out = vec.chain(raw, B, P, R, C, ("single", ref), cfar, near_tol=RTOL, dbf=W)
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=1) as ctx:
+        ctx.set_dbf(W)
+        rdm, dets, n = ctx.chain(raw, B)
+        assert rdm.shape == (B, NB, P, R)
+        pc = ctx.debug_fetch_pc(0)
+        _close(pc, out["pc"][B - 1])
+        _close(rdm, out["rdm"])
+        _compare_flags(dets, out, B, NB, P, R, lib)
+        ctx.set_dbf(None)                                    # back to per-channel processing
+        rdm16, _, _ = ctx.chain(raw, B)
+        assert rdm16.shape == (B, C, P, R)
+        _close(rdm16, vec.chain(raw, B, P, R, C, ("single", ref), cfar)["rdm"])

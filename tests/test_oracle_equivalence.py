@@ -218,3 +218,18 @@ def test_synth_s3_wire_and_chain_tiny():
     for lane, r0, k, snr in tg[0]:
         assert out["flag"][0, lane, k + 32, max(r0 - 1, 0):r0 + 2].sum() >= 1, (lane, r0, k, snr)
     assert np.all(out["rdm"][0, :, 31, :] == 0)
+
+
+def test_dbf_weighting_matches_per_prt_matrix_product():
+    # FrameDataRead_xzr.m:156-158: current_sig_data_DBF = sig_data_C * DBF_coeffs_data_C.'  (n x 16) * (16 x 13)
+    rng = np.random.default_rng(21)
+    P, R, C, NB = 3, 50, 16, 13
+    raw = rng.integers(-2000, 2000, size=(1, P, R, C, 2), dtype=np.int16)
+    W = _rand_c(rng, NB, C)
+    x = vec.unpack_wire(raw, 1, P, R, C)
+    beams = vec.dbf_weighting(x, W)
+    assert beams.shape == (1, NB, P, R)
+    for p in range(P):
+        sig_c = mcode.unpack_ddc_i16(np.frombuffer(raw[0, p].tobytes(), dtype=np.uint8), R, C)      # n x 16
+        want = sig_c @ W.T                                                                         # non-conjugate transpose
+        assert np.allclose(beams[0, :, p, :].T, want, rtol=0, atol=1e-9)
