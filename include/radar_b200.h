@@ -217,6 +217,14 @@ int rb200_get_stage_ms(rb200_ctx* ctx, float ms[3], int* n_chunks, int* n_cpis);
  * (rdm_out [cpi][beam][v][range], rb200_det.lane) is a beam index and buffers are sized with n_beams.   */
 int rb200_set_dbf(rb200_ctx* ctx, const double* w_re, const double* w_im, int n_beams);
 
+/* f1: unpack of DBF-type (data_type 2) PRT payloads: 24-bit little-endian I/Q words, rows of
+ * n_channels*6 + one_sample_pad bytes, each PRT payload padded to 64 B (FrameDataRead_xzr.m:111-119,130-135,163).
+ * bytes: n_prt concatenated payloads (host).  out_ri: float2 [column][prt][sample] with
+ * *n_columns = number of complex columns the M-code's slicing produces (n_channels, or one more when the
+ * per-sample padding is 8 bytes).  Values are exact (|v| <= 2^23); 0x800000 decodes to +8388608 as in the M-code. */
+int rb200_unpack_dbf24(rb200_ctx* ctx, const uint8_t* bytes, int n_prt, int n_samples, int n_channels,
+                       float* out_ri, int* n_columns);
+
 #ifdef __cplusplus
 }
 #endif

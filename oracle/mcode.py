@@ -138,6 +138,40 @@ def unpack_ddc_i16(signal_data_raw, pulse_data_num, channel_num):
     return I + 1j * Q                                                    # :156
 
 
+def dbf24_payload_size(pulse_data_num, channel_num):
+    """(sig_data_size, pad_size, one_sample_pad) in bytes for data_type==2.  FrameDataRead_xzr.m:111-119."""
+    one_sample_pad = 8 - (6 * channel_num) % 8                              # :111 (8, not 0, when already aligned)
+    sig = pulse_data_num * channel_num * 2 * 3 + pulse_data_num * one_sample_pad
+    pad = (64 - sig % 64) if sig % 64 > 0 else 0
+    return sig, pad, one_sample_pad
+
+
+def unpack_dbf24(signal_data_raw, pulse_data_num, channel_num):
+    """One DBF-type PRT payload (uint8 bytes incl. padding) -> (pulse_data_num, ncol) complex128.
+
+    FrameDataRead_xzr.m:130-135,163: rows of ``channel_num*6 + one_sample_pad`` bytes, 3-byte little-endian
+    words, ``> 2^23`` (not ``>=``) mapped to negative, I = cols 1:2:end, Q = cols 2:2:end.
+    DEVIATION, stated: the M-code does this arithmetic on ``uint8`` data (read_continuous_file_stream.m:89 reads
+    ``*uint8``), which saturates at 255 -- the source comment at :130 says the block "has problems, not fixed
+    yet".  The restatement widens the bytes to double first, i.e. implements the 24-bit format the comment
+    describes, and keeps the ``> 2^23`` quirk (0x800000 decodes to +8388608).
+    """
+    sig, pad, osp = dbf24_payload_size(pulse_data_num, channel_num)
+    raw = np.ascontiguousarray(signal_data_raw, dtype=np.uint8).ravel()
+    W = channel_num * 2 * 3 + osp
+    data_temp = raw[: raw.size - pad].astype(np.float64).reshape(-1, W)      # :132 reshape(W,[]).'
+    c1 = np.arange(1, W - 3 + 1, 3)                                         # 1:3:end-3
+    c2 = np.arange(2, W - 2 + 1, 3)                                         # 2:3:end-2
+    c3 = np.arange(3, W + 1, 3)                                             # 3:3:end
+    if not (c1.size == c2.size == c3.size):
+        raise MatlabError("MATLAB:sizeDimensionsMustMatch", "Arrays have incompatible sizes for this operation")
+    parsed = data_temp[:, c1 - 1] + data_temp[:, c2 - 1] * 2 ** 8 + data_temp[:, c3 - 1] * 2 ** 16     # :133
+    parsed[parsed > 2 ** 23] -= 2 ** 24                                     # :134-135
+    if parsed.shape[1] % 2:
+        raise MatlabError("MATLAB:sizeDimensionsMustMatch", "Arrays have incompatible sizes for this operation")
+    return parsed[:, 0::2] + 1j * parsed[:, 1::2]                           # :163
+
+
 # ----------------------------------------------------------------------------------------------
 # A4  fun_pulse_compression  (MP/fun_pulse_compression.m:1-24)
 # ----------------------------------------------------------------------------------------------

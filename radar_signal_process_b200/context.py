@@ -171,6 +171,16 @@ class Context:
         self._ck(self._lib.rb200_unpack_ddc_i16(self._h, raw.ctypes.data, n_cpi, out.ctypes.data))
         return out
 
+    def unpack_dbf24(self, payload_bytes, n_prt, n_samples, n_channels):
+        """DBF-type (24-bit) PRT payloads -> complex64 [column][prt][sample] (FrameDataRead_xzr.m:130-135,163)."""
+        b = np.ascontiguousarray(payload_bytes, dtype=np.uint8)
+        osp = 8 - (6 * n_channels) % 8
+        ncol_max = (6 * n_channels + osp) // 6 + 1
+        out = np.zeros((ncol_max, n_prt, n_samples), dtype=np.complex64)
+        ncol = C.c_int(0)
+        self._ck(self._lib.rb200_unpack_dbf24(self._h, b.ctypes.data, int(n_prt), int(n_samples), int(n_channels), out.ctypes.data, C.byref(ncol)))
+        return out.reshape(-1)[: ncol.value * n_prt * n_samples].reshape(ncol.value, n_prt, n_samples).copy()
+
     def chain(self, raw, n_cpi, want_rdm=True, allow_overflow=False):
         """Host-buffer chain call: numpy int16 wire array in, (rdm float32 [cpi][lane][v][r] | None, dets) out."""
         c = self.cfg

@@ -952,6 +952,30 @@ extern "C" int rb200_unpack_ddc_i16(rb200_ctx* c, const int16_t* raw, int n_cpi,
     return RB200_OK;
 }
 
+extern "C" int rb200_unpack_dbf24(rb200_ctx* c, const uint8_t* bytes, int n_prt, int n, int n_ch, float* out_ri, int* n_columns) {
+    if (!c || !bytes || !out_ri || n_prt < 1 || n < 1 || n_ch < 1) return fail(c, RB200_ERR_ARG, "unpack_dbf24: bad argument");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    const int osp = 8 - (6 * n_ch) % 8;                                   // FrameDataRead_xzr.m:111
+    const int W = 6 * n_ch + osp;
+    const size_t sig = (size_t)n * W;                                     // :112
+    const size_t prt_bytes = sig + ((sig % 64) ? 64 - sig % 64 : 0);      // :115-119
+    // column counts of 1:3:end-3, 2:3:end-2, 3:3:end must agree (MATLAB would raise otherwise)
+    const int n1 = (W - 3 >= 1) ? (W - 3 - 1) / 3 + 1 : 0, n2 = (W - 2 >= 2) ? (W - 2 - 2) / 3 + 1 : 0, n3 = (W >= 3) ? (W - 3) / 3 + 1 : 0;
+    if (n1 != n2 || n2 != n3 || (n1 % 2)) return fail(c, RB200_ERR_DIM_MISMATCH, "frameDataRead: arrays have incompatible sizes (24-bit word slicing)");
+    const int ncol = n1 / 2;
+    if (n_columns) *n_columns = ncol;
+    const size_t in_bytes = prt_bytes * n_prt, out_elems = (size_t)ncol * n_prt * n;
+    CK(c, c->raw.ensure(in_bytes));
+    CK(c, c->s_a.ensure(out_elems * sizeof(float2)));
+    CK(c, cudaMemcpyAsync(c->raw.p, bytes, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(c, launch_unpack_dbf24(c->raw.as<uint8_t>(), c->s_a.as<float2>(), n_prt, n, ncol, W, prt_bytes, c->stream));
+    c->launches++;
+    CK(c, cudaMemcpyAsync(out_ri, c->s_a.p, out_elems * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RB200_OK;
+}
+
 static int chunk_size(const rb200_ctx* c) {
     const char* env = getenv("RB200_CHUNK");
     int g = env ? atoi(env) : c->cfg.chunk_cpi;

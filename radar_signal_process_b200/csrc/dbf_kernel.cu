@@ -60,6 +60,33 @@ dbf_kernel(const int* __restrict__ raw, float2* __restrict__ out, const float2* 
     }
 }
 
+// DBF-type (data_type 2) payload: rows of row_bytes bytes per range sample, 3-byte little-endian words,
+// value > 2^23 -> value - 2^24 (FrameDataRead_xzr.m:130-135,163).  One thread per output complex value.
+// out: float2 planar [beam][prt][range].
+__global__ void unpack_dbf24_kernel(const uint8_t* __restrict__ bytes, float2* __restrict__ out, int n_prt, int n, int ncol,
+                                    int row_bytes, size_t prt_bytes) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n_prt * n * ncol;
+    if (i >= total) return;
+    const int r = (int)(i % n);
+    const size_t t1 = i / n;
+    const int prt = (int)(t1 % n_prt);
+    const int b = (int)(t1 / n_prt);
+    const uint8_t* q = bytes + (size_t)prt * prt_bytes + (size_t)r * row_bytes + (size_t)b * 6;
+    int vi = (int)q[0] | ((int)q[1] << 8) | ((int)q[2] << 16);
+    int vq = (int)q[3] | ((int)q[4] << 8) | ((int)q[5] << 16);
+    if (vi > (1 << 23)) vi -= (1 << 24);
+    if (vq > (1 << 23)) vq -= (1 << 24);
+    out[i] = make_float2((float)vi, (float)vq);       // |v| <= 2^23: exact in fp32
+}
+
+cudaError_t launch_unpack_dbf24(const uint8_t* bytes, float2* out, int n_prt, int n, int ncol, int row_bytes, size_t prt_bytes, cudaStream_t st) {
+    const size_t total = (size_t)n_prt * n * ncol;
+    if (total == 0) return cudaSuccess;
+    unpack_dbf24_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bytes, out, n_prt, n, ncol, row_bytes, prt_bytes);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_dbf(const int16_t* raw, float2* out, const float2* W, int n_beams, int n_ch, int n_groups, int P, int R, cudaStream_t st) {
     if (n_groups <= 0 || n_beams <= 0) return cudaSuccess;
     if (n_groups > 65535) return cudaErrorInvalidConfiguration;

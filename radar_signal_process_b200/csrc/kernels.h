@@ -21,6 +21,8 @@ cudaError_t launch_unpack(const int16_t* raw, float2* out, int n_groups, int P, 
 // ---- DBF weighting fused with the unpack (dbf_kernel.cu): wire int16 -> float2 planar [cpi][beam][prt][range]
 cudaError_t launch_dbf(const int16_t* raw, float2* out, const float2* W, int n_beams, int n_ch, int n_groups, int P, int R, cudaStream_t st);
 
+cudaError_t launch_unpack_dbf24(const uint8_t* bytes, float2* out, int n_prt, int n, int ncol, int row_bytes, size_t prt_bytes, cudaStream_t st);
+
 // ---- K2 MTD (mtd_kernels.cu)
 bool mtd_has_fast_path(int P);
 cudaError_t launch_mtd(const MtdParams& p, int n_slabs, cudaStream_t st);

@@ -506,3 +506,17 @@ def test_chain_with_dbf_weighting(lib):
         rdm16, _, _ = ctx.chain(raw, B)
         assert rdm16.shape == (B, C, P, R)
         _close(rdm16, vec.chain(raw, B, P, R, C, ("single", ref), cfar)["rdm"])
+
+
+@pytest.mark.parametrize("ch,n,n_prt", [(13, 37, 3), (4, 16, 2), (16, 5, 1)])
+def test_unpack_dbf24_bit_exact(lib, ch, n, n_prt):
+    rng = np.random.default_rng(ch)
+    sig, pad, osp = mcode.dbf24_payload_size(n, ch)
+    payloads = rng.integers(0, 256, size=(n_prt, sig + pad), dtype=np.uint8)
+    payloads[0, 0:6] = (0, 0, 0x80, 1, 0, 0x80)                  # 0x800000 -> +2^23 (quirk), 0x800001 -> -(2^23-1)
+    with lib.Context(0) as ctx:
+        got = ctx.unpack_dbf24(payloads, n_prt, n, ch)
+    want = np.stack([mcode.unpack_dbf24(payloads[p], n, ch) for p in range(n_prt)], axis=0)      # prt, sample, col
+    assert got.shape == (want.shape[2], n_prt, n)
+    assert np.array_equal(got.astype(np.complex128), want.transpose(2, 0, 1))
+    assert got[0, 0, 0] == 8388608 - 8388607j

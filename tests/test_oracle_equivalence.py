@@ -233,3 +233,28 @@ def test_dbf_weighting_matches_per_prt_matrix_product():
         sig_c = mcode.unpack_ddc_i16(np.frombuffer(raw[0, p].tobytes(), dtype=np.uint8), R, C)      # n x 16
         want = sig_c @ W.T                                                                         # non-conjugate transpose
         assert np.allclose(beams[0, :, p, :].T, want, rtol=0, atol=1e-9)
+
+
+def test_unpack_dbf24_known_words():
+    # FrameDataRead_xzr.m:111-119,130-135: 13 beams -> 78 data bytes + 2 pad bytes per sample; > 2^23 goes negative
+    assert mcode.dbf24_payload_size(3404, 13) == (3404 * 80, (64 - (3404 * 80) % 64) % 64, 2)
+    words = {0x000001: 1, 0x7FFFFF: 8388607, 0x800000: 8388608, 0x800001: -8388607, 0xFFFFFF: -1, 0x000000: 0}
+    ch, n = 13, 2
+    sig, pad, osp = mcode.dbf24_payload_size(n, ch)
+    payload = np.zeros(sig + pad, dtype=np.uint8)
+    keys = list(words)
+    for r in range(n):
+        for v in range(2 * ch):
+            w = keys[(r * 7 + v) % len(keys)]
+            o = r * (6 * ch + osp) + 3 * v
+            payload[o:o + 3] = (w & 255, (w >> 8) & 255, (w >> 16) & 255)
+    z = mcode.unpack_dbf24(payload, n, ch)
+    assert z.shape == (n, ch)
+    for r in range(n):
+        for b in range(ch):
+            assert z[r, b].real == words[keys[(r * 7 + 2 * b) % len(keys)]]
+            assert z[r, b].imag == words[keys[(r * 7 + 2 * b + 1) % len(keys)]]
+    # aligned case keeps the 8-byte per-sample padding and yields one extra (zero) column, as the M slicing does
+    assert mcode.dbf24_payload_size(4, 4)[2] == 8
+    z4 = mcode.unpack_dbf24(np.zeros(sum(mcode.dbf24_payload_size(4, 4)[:2]), dtype=np.uint8), 4, 4)
+    assert z4.shape == (4, 5)
