@@ -217,6 +217,15 @@ int rb200_get_stage_ms(rb200_ctx* ctx, float ms[3], int* n_chunks, int* n_cpis);
  * (rdm_out [cpi][beam][v][range], rb200_det.lane) is a beam index and buffers are sized with n_beams.   */
 int rb200_set_dbf(rb200_ctx* ctx, const double* w_re, const double* w_im, int n_beams);
 
+/* f4: sliding-window CPI assembly with the pulse compression done once (MP/main_produce_dataset_win_xzr.m:24-38:
+ * echo_win = [frame N; frame N+1], window i = rows round(i*P/n)+1 ... +P, fun_MTD_produce per window).
+ * Pulse compression is per PRT and therefore identical for every window a PRT belongs to; this entry point
+ * compresses the P_total rows once and runs MTD + 0-v on n_win windows of win_len rows starting at
+ * row_start[i] (0-based).  echo: P_total x R column-major split double; out: n_win consecutive win_len x R
+ * column-major real matrices.  Equivalent to n_win calls of rb200_mtd_produce_z on the row slices.        */
+int rb200_mtd_produce_windows_z(rb200_ctx* ctx, const double* echo_re, const double* echo_im, int P_total, int R,
+                                int win_len, const int32_t* row_start, int n_win, double beta, int zero_v_div, double* out);
+
 /* f1: unpack of DBF-type (data_type 2) PRT payloads: 24-bit little-endian I/Q words, rows of
  * n_channels*6 + one_sample_pad bytes, each PRT payload padded to 64 B (FrameDataRead_xzr.m:111-119,130-135,163).
  * bytes: n_prt concatenated payloads (host).  out_ri: float2 [column][prt][sample] with

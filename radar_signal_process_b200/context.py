@@ -134,6 +134,20 @@ class Context:
         self._ck(self._lib.rb200_mtd_produce_z(self._h, _fptr(re), _fptr(im), P, R, float(beta), int(zero_v_div), _fptr(out)))
         return out
 
+    def mtd_produce_windows(self, echo, win_len, row_start, beta=8.0, zero_v_div=150):
+        """PC once over all rows, MTD + 0-v per window (rows row_start[i] .. row_start[i]+win_len-1, 0-based)."""
+        echo = np.atleast_2d(echo)
+        P, R = echo.shape
+        re, im = _split(echo)
+        rs = np.ascontiguousarray(row_start, dtype=np.int32)
+        out = np.zeros((rs.size, int(win_len), R), dtype=np.float64)
+        buf = np.zeros(rs.size * int(win_len) * R)
+        self._ck(self._lib.rb200_mtd_produce_windows_z(self._h, _fptr(re), _fptr(im), P, R, int(win_len), rs.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                       rs.size, float(beta), int(zero_v_div), _fptr(buf)))
+        for i in range(rs.size):
+            out[i] = buf[i * win_len * R:(i + 1) * win_len * R].reshape((int(win_len), R), order="F")
+        return out
+
     def cfar1d_sub(self, data, ref, guard, T, method):
         d = np.asfortranarray(np.atleast_2d(data), dtype=np.float64)
         out = np.zeros(d.shape, order="F")

@@ -824,6 +824,39 @@ extern "C" int rb200_mtd_produce_z(rb200_ctx* c, const double* echo_re, const do
     return RB200_OK;
 }
 
+extern "C" int rb200_mtd_produce_windows_z(rb200_ctx* c, const double* echo_re, const double* echo_im, int P_total, int R, int win_len,
+                                           const int32_t* row_start, int n_win, double beta, int zero_v_div, double* out) {
+    if (!c || !echo_re || !row_start || !out || P_total < 1 || R < 1 || win_len < 1 || n_win < 1)
+        return fail(c, RB200_ERR_ARG, "mtd_produce_windows: bad argument");
+    for (int i = 0; i < n_win; ++i)
+        if (row_start[i] < 0 || row_start[i] + win_len > P_total)
+            return fail(c, RB200_ERR_INDEX, "main_produce_dataset_win: Index in position 1 exceeds array bounds (window past the last PRT)");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    const size_t n = (size_t)P_total * R, nw = (size_t)win_len * R;
+    const double *dre, *dim;
+    int rc = upload_z(c, echo_re, echo_im, n, &dre, &dim);
+    if (rc) return rc;
+    CK(c, c->s_a.ensure(n * sizeof(float2)));
+    CK(c, c->s_b.ensure(n * sizeof(float2)));
+    CK(c, c->s_c.ensure(nw * sizeof(float)));
+    CK(c, c->s_out_re.ensure(nw * sizeof(double)));
+    CK(c, launch_z_to_planar(dre, dim, c->s_a.as<float2>(), P_total, R, c->stream));
+    c->launches++;
+    rc = run_pc(c, c->plan, false, c->s_a.p, c->s_b.as<float2>(), R, R, 1, 1, 0, P_total, nullptr, c->stream);   // once for all windows
+    if (rc) return rc;
+    for (int i = 0; i < n_win; ++i) {
+        rc = run_mtd(c, c->s_b.as<float2>() + (size_t)row_start[i] * R, c->s_c.as<float>(), win_len, R, R, R, 1, beta, zero_v_div,
+                     c->cfg.mti_lag, c->stream);
+        if (rc) return rc;
+        CK(c, launch_f32_rowmajor_to_d_colmajor(c->s_c.as<float>(), c->s_out_re.as<double>(), win_len, R, c->stream));
+        c->launches++;
+        CK(c, cudaMemcpyAsync(out + (size_t)i * nw, c->s_out_re.p, nw * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RB200_OK;
+}
+
 static int fetch_errflag(rb200_ctx* c, const char* what) {
     CK(c, cudaMemcpyAsync(c->h_counts + 3, c->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));

@@ -108,6 +108,17 @@ def fun_MTD_produce(echo, params=None):
     return ctx.mtd_produce(echo, 8.0, 150)
 
 
+def fun_MTD_produce_windows(echo_win, win_len=1536, win_size=4):
+    """The window loop of MP/main_produce_dataset_win_xzr.m:31-38 in one call: window i covers rows
+    round(i*win_len/win_size)+1 ... +win_len of ``echo_win`` (two concatenated frames); pulse compression
+    is done once for all rows.  Returns ``MTD[i, :, :]`` = ``fun_MTD_produce(echo_win(rows_i, :))``."""
+    echo_win = np.atleast_2d(echo_win)
+    n = echo_win.shape[1]
+    ctx = _set_plan(("mp", n) + _key(W.PULSE2, W.PULSE3), lambda: W.segments_mp(n, W.PULSE2, W.PULSE3))
+    starts = [int(np.floor(i * win_len / win_size + 0.5)) for i in range(win_size)]      # MATLAB round
+    return ctx.mtd_produce_windows(echo_win, win_len, starts, 8.0, 150)
+
+
 def executeCFAR(mtd, refCells_R, saveCells_R, T_CFAR_R, CFARmethod_R, refCells_V, saveCells_V, T_CFAR_V, CFARmethod_V,
                 MTD_0_num, rCFARDetect_Flag):
     return default_context().execute_cfar(mtd, refCells_R, saveCells_R, T_CFAR_R, CFARmethod_R, refCells_V, saveCells_V,

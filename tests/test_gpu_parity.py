@@ -520,3 +520,24 @@ def test_unpack_dbf24_bit_exact(lib, ch, n, n_prt):
     assert got.shape == (want.shape[2], n_prt, n)
     assert np.array_equal(got.astype(np.complex128), want.transpose(2, 0, 1))
     assert got[0, 0, 0] == 8388608 - 8388607j
+
+
+def test_sliding_window_reuse_matches_per_window_calls(lib):
+    """the 4-window loop of MP/main_produce_dataset_win_xzr.m:24-38 with the pulse compression
+    done once over the concatenated frames equals fun_MTD_produce on every window slice."""
+    rng = np.random.default_rng(41)
+    win_len, win_size, n = 256, 4, 1031
+    echo_win = np.rint(150 * _rand_c(rng, 2 * win_len, n))                     # [frame N; frame N+1]
+    got = lib.fun_MTD_produce_windows(echo_win, win_len, win_size)
+    assert got.shape == (win_size, win_len, n)
+    for i in range(win_size):
+        s0 = mcode.mround(i * win_len / win_size)                              # round(i*1536/win_size)+1 (1-based)
+        want = mcode.fun_MTD_produce_mp(echo_win[s0:s0 + win_len]) if i == 1 else None
+        one = lib.fun_MTD_produce(echo_win[s0:s0 + win_len])
+        assert np.array_equal(got[i], one)                                     # same kernels, same data -> same bits
+        if want is not None:
+            _close(got[i], want)
+    with lib.Context(0) as ctx:
+        ctx.set_waveform(lib.waveforms.segments_mp(n, lib.waveforms.PULSE2, lib.waveforms.PULSE3))
+        with pytest.raises(lib.MatlabIndexError):
+            ctx.mtd_produce_windows(echo_win, win_len, [0, 2 * win_len - 10])
