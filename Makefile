@@ -5,13 +5,13 @@ PKG       := radar_signal_process_b200
 CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libradar_b200.so
 NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas --expt-relaxed-constexpr
-CU_SRCS   := $(CSRC)/api.cu $(CSRC)/pc_kernels.cu $(CSRC)/mtd_kernels.cu $(CSRC)/mtd64_kernel.cu $(CSRC)/chain64_kernel.cu $(CSRC)/dbf_kernel.cu $(CSRC)/cfar_kernels.cu $(CSRC)/layout_kernels.cu
+CU_SRCS   := $(CSRC)/api.cu $(CSRC)/pc_kernels.cu $(CSRC)/mtd_kernels.cu $(CSRC)/mtd64_kernel.cu $(CSRC)/chain64_kernel.cu $(CSRC)/dbf_kernel.cu $(CSRC)/measure_kernels.cu $(CSRC)/cfar_kernels.cu $(CSRC)/layout_kernels.cu
 CU_OBJS   := $(CU_SRCS:.cu=.o)
 HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/radar_b200.h
 
 MEXDIR    := mex
 MEXBUILD  := mex/build
-MEX_NAMES := fun_MTD_produce fun_lss_pulse_compression fun_pulse_compression fun_Process_MTD fun_0v_pressing executeCFAR Function_CFAR1D_sub Function_CFAR1D_sub_fixCells
+MEX_NAMES := motionParaMeasure fun_MTD_produce fun_lss_pulse_compression fun_pulse_compression fun_Process_MTD fun_0v_pressing executeCFAR Function_CFAR1D_sub Function_CFAR1D_sub_fixCells
 MEX_SOS   := $(addprefix $(MEXBUILD)/,$(addsuffix .so,$(MEX_NAMES))) $(MEXBUILD)/fun_0v_pressing_cw.so
 SHIM      := $(MEXBUILD)/librbmexshim.so
 MEXFLAGS  := -O2 -fPIC -shared -Wall -I$(MEXDIR)/shim -I$(MEXDIR) -Wno-unused-function

@@ -217,6 +217,19 @@ int rb200_get_stage_ms(rb200_ctx* ctx, float ms[3], int* n_chunks, int* n_cpis);
  * (rdm_out [cpi][beam][v][range], rb200_det.lane) is a beam index and buffers are sized with n_beams.   */
 int rb200_set_dbf(rb200_ctx* ctx, const double* w_re, const double* w_im, int n_beams);
 
+/* f3: [rEst, vEst, eleEst] = motionParaMeasure(sum, diff, flags, extraDots, rScale, deltaR, rInterpTimes, vScale, deltaV,
+ *          vInterpTimes, kValues, beamPosNum, beamAngleStep, freInd, eleAngleComp, eleAngleSysErr, MTD_0_num)
+ * Replaces CW/motionParaMeasure.m:1.  sum / diff / flags: V x R column-major double; r_scale: R values; v_scale: V
+ * values; k_values: k_rows x k_cols column-major (angle_KvalueGen.m).  Outputs hold one value per flagged cell in
+ * MATLAB find() order; capacity = room in each output array; *n_out = number of flagged cells (RB200_ERR_OVERFLOW
+ * if larger than capacity).  extra_dots <= 16.                                                                  */
+int rb200_motion_para_measure_d(rb200_ctx* ctx, const double* mtd_sum, const double* mtd_diff, const double* flags, int V, int R,
+                                int extra_dots, const double* r_scale, double delta_r, int r_interp_times,
+                                const double* v_scale, double delta_v, int v_interp_times,
+                                const double* k_values, int k_rows, int k_cols, double beam_pos_num, double beam_angle_step,
+                                int fre_ind, double ele_angle_comp, double ele_angle_sys_err, int mtd_0_num,
+                                double* out_r, double* out_v, double* out_ele, int capacity, int* n_out);
+
 /* f4: sliding-window CPI assembly with the pulse compression done once (MP/main_produce_dataset_win_xzr.m:24-38:
  * echo_win = [frame N; frame N+1], window i = rows round(i*P/n)+1 ... +P, fun_MTD_produce per window).
  * Pulse compression is per PRT and therefore identical for every window a PRT belongs to; this entry point

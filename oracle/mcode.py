@@ -494,3 +494,69 @@ def fun_CFARflag(MTD_data, refCells_R, saveCells_R, T_CFAR_R, CFARmethod_R, refC
                            refCells_V, saveCells_V, T_CFAR_V, CFARmethod_V, MTD_0_num, rCFARDetect_Flag)
         out[:, a - 1:b] = f                                              # :157-159
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# f3  motionParaMeasure  (CW/motionParaMeasure.m:1-88) -- post-CFAR range / velocity / elevation measurement
+# ----------------------------------------------------------------------------------------------
+def matlab_spline_eval(y, xq):
+    """``interp1(0:n-1, y, xq, 'spline')``: not-a-knot cubic spline (MATLAB ``spline``); n = 2 -> line, n = 3 -> parabola."""
+    from scipy.interpolate import CubicSpline
+    y = np.asarray(y, dtype=np.float64)
+    n = y.size
+    x = np.arange(n, dtype=np.float64)
+    if n == 1:
+        return np.full(np.shape(xq), y[0])
+    if n == 2:
+        return y[0] + (y[1] - y[0]) * np.asarray(xq)
+    return CubicSpline(x, y, bc_type="not-a-knot")(np.asarray(xq))
+
+
+def motionParaMeasure(mtd_sum, mtd_diff, flags, extraDots, rScale, deltaR, rInterpTimes, vScale, deltaV, vInterpTimes,
+                      kValues, beamPosNum, beamAngleStep, freInd, eleAngleComp, eleAngleSysErr, MTD_0_num):
+    mtd_sum = np.asarray(mtd_sum, dtype=np.float64)
+    mtd_diff = np.asarray(mtd_diff, dtype=np.float64)
+    flags = np.asarray(flags)
+    vCellNum, rCellNum = flags.shape                                      # :5
+    cc, rr = np.nonzero(flags.T)                                          # :6 find(): column-major
+    vInd, rInd = rr + 1, cc + 1
+    k = int(extraDots)
+    ext = np.arange(-k, k + 1)                                            # :8
+    rEst, vEst, eEst = [], [], []
+    for mm in range(vInd.size):                                           # :17
+        v, r = int(vInd[mm]), int(rInd[mm])
+        cells = ext + r                                                   # :22
+        if cells.min() <= 0:                                              # :24-27
+            cells = 1 + np.arange(0, 2 * k + 1)
+        if cells.max() > rCellNum:                                        # :29-32
+            cells = rCellNum - np.arange(0, 2 * k + 1)
+        cells = np.sort(cells)                                            # :33
+        if cells.min() < 1 or cells.max() > rCellNum:
+            raise MatlabError("MATLAB:badsubscript", "Index exceeds array bounds")
+        data = mtd_sum[v - 1, cells - 1]                                  # :36
+        nq = int(math.floor((cells[-1] - cells[0]) * rInterpTimes + 1e-9)) + 1
+        xq = cells[0] + np.arange(nq) / float(rInterpTimes)               # :37
+        dq = matlab_spline_eval(data, xq - cells[0])                      # :38
+        rCellMax = xq[int(np.argmax(dq))]                                 # :39-42
+        r_est = rScale[r - 1] + (rCellMax - r) * deltaR                   # :43
+        cells = ext + v                                                   # :49
+        if cells.min() <= MTD_0_num + 1:                                  # :51-54
+            cells = (MTD_0_num + 2) + np.arange(0, 2 * k + 1)
+        if cells.max() > vCellNum - MTD_0_num:                            # :56-59
+            cells = (vCellNum - MTD_0_num) - np.arange(0, 2 * k + 1)
+        cells = np.sort(cells)                                            # :60
+        if cells.min() < 1 or cells.max() > vCellNum:
+            raise MatlabError("MATLAB:badsubscript", "Index exceeds array bounds")
+        data = mtd_sum[cells - 1, r - 1]                                  # :63
+        nq = int(math.floor((cells[-1] - cells[0]) * vInterpTimes + 1e-9)) + 1
+        xq = cells[0] + np.arange(nq) / float(vInterpTimes)               # :64
+        dq = matlab_spline_eval(data, xq - cells[0])                      # :65
+        vCellMax = xq[int(np.argmax(dq))]                                 # :66-69
+        fx = int(np.fix(vCellMax))
+        v_est = vScale[fx - 1] - (vCellMax - fx) * deltaV                 # :70
+        ratio = mtd_diff[v - 1, r - 1] / mtd_sum[v - 1, r - 1]            # :76-78
+        e_est = beamPosNum * beamAngleStep + 2.5 - ratio * kValues[int(freInd), int(beamPosNum)] + eleAngleComp + eleAngleSysErr   # :79
+        rEst.append(r_est)
+        vEst.append(v_est)
+        eEst.append(e_est)
+    return np.array(rEst), np.array(vEst), np.array(eEst)

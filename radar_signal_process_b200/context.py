@@ -148,6 +148,25 @@ class Context:
             out[i] = buf[i * win_len * R:(i + 1) * win_len * R].reshape((int(win_len), R), order="F")
         return out
 
+    def motion_para_measure(self, mtd_sum, mtd_diff, flags, extraDots, rScale, deltaR, rInterpTimes, vScale, deltaV, vInterpTimes,
+                            kValues, beamPosNum, beamAngleStep, freInd, eleAngleComp, eleAngleSysErr, MTD_0_num):
+        s = np.asfortranarray(np.atleast_2d(mtd_sum), dtype=np.float64)
+        d = np.asfortranarray(np.atleast_2d(mtd_diff), dtype=np.float64)
+        f = np.asfortranarray(np.atleast_2d(flags), dtype=np.float64)
+        V, R = f.shape
+        rs = np.ascontiguousarray(rScale, dtype=np.float64).ravel()
+        vs = np.ascontiguousarray(vScale, dtype=np.float64).ravel()
+        kv = np.asfortranarray(np.atleast_2d(kValues), dtype=np.float64)
+        cap = int(np.count_nonzero(f))
+        outs = [np.zeros(max(cap, 1)) for _ in range(3)]
+        n = C.c_int(0)
+        self._ck(self._lib.rb200_motion_para_measure_d(self._h, _fptr(s), _fptr(d), _fptr(f), V, R, int(extraDots), _fptr(rs), float(deltaR),
+                                                       int(rInterpTimes), _fptr(vs), float(deltaV), int(vInterpTimes), _fptr(kv), kv.shape[0],
+                                                       kv.shape[1], float(beamPosNum), float(beamAngleStep), int(freInd), float(eleAngleComp),
+                                                       float(eleAngleSysErr), int(MTD_0_num), _fptr(outs[0]), _fptr(outs[1]), _fptr(outs[2]),
+                                                       cap, C.byref(n)))
+        return tuple(o[: n.value].copy() for o in outs)
+
     def cfar1d_sub(self, data, ref, guard, T, method):
         d = np.asfortranarray(np.atleast_2d(data), dtype=np.float64)
         out = np.zeros(d.shape, order="F")

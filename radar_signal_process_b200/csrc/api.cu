@@ -1009,6 +1009,56 @@ extern "C" int rb200_unpack_dbf24(rb200_ctx* c, const uint8_t* bytes, int n_prt,
     return RB200_OK;
 }
 
+extern "C" int rb200_motion_para_measure_d(rb200_ctx* c, const double* mtd_sum, const double* mtd_diff, const double* flags, int V, int R,
+                                           int extra, const double* r_scale, double delta_r, int r_times, const double* v_scale,
+                                           double delta_v, int v_times, const double* k_values, int k_rows, int k_cols,
+                                           double beam_pos, double beam_step, int fre_ind, double ele_comp, double ele_err, int n0,
+                                           double* out_r, double* out_v, double* out_e, int capacity, int* n_out) {
+    if (!c || !mtd_sum || !mtd_diff || !flags || !r_scale || !v_scale || !k_values || !n_out || V < 1 || R < 1 || extra < 0 ||
+        r_times < 1 || v_times < 1 || capacity < 0 || k_rows < 1 || k_cols < 1)
+        return fail(c, RB200_ERR_ARG, "motionParaMeasure: bad argument");
+    if (extra > 16) return fail(c, RB200_ERR_UNSUPPORTED, "motionParaMeasure: extraDots > 16 is not supported");
+    if (fre_ind < 0 || fre_ind >= k_rows || beam_pos < 0 || (int)beam_pos >= k_cols)
+        return fail(c, RB200_ERR_INDEX, "motionParaMeasure: kValues(freInd+1, beamPosNum+1) exceeds array bounds");
+    if (2 * extra + 1 > R || 2 * extra + 1 > V - 2 * n0 - 1)
+        return fail(c, RB200_ERR_INDEX, "motionParaMeasure: Index exceeds array bounds (fewer cells than 2*extraDots+1)");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    const size_t n = (size_t)V * R;
+    // device copies: [sum | diff | flags | rScale | vScale | kValues]
+    const size_t nd = 3 * n + R + V + (size_t)k_rows * k_cols;
+    CK(c, c->s_in_re.ensure(nd * sizeof(double)));
+    double* d = c->s_in_re.as<double>();
+    double *d_sum = d, *d_diff = d + n, *d_flags = d + 2 * n, *d_rs = d + 3 * n, *d_vs = d_rs + R, *d_k = d_vs + V;
+    CK(c, cudaMemcpyAsync(d_sum, mtd_sum, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(d_diff, mtd_diff, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(d_flags, flags, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(d_rs, r_scale, R * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(d_vs, v_scale, V * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(d_k, k_values, (size_t)k_rows * k_cols * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(c, c->s_idx.ensure((size_t)(R + 1) * sizeof(int)));
+    int* col_start = c->s_idx.as<int>();
+    CK(c, cudaMemsetAsync(c->errflag.p, 0, sizeof(int), c->stream));
+    CK(c, launch_flag_compaction(d_flags, V, R, col_start, col_start + R, c->stream));
+    c->launches += 2;
+    CK(c, cudaMemcpyAsync(c->h_counts, col_start + R, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    const int total = c->h_counts[0];
+    *n_out = total;
+    if (total == 0) return RB200_OK;
+    if (total > capacity) return fail(c, RB200_ERR_OVERFLOW, "motionParaMeasure: more flagged cells than the output capacity");
+    if (!out_r || !out_v || !out_e) return fail(c, RB200_ERR_ARG, "motionParaMeasure: output arrays are NULL");
+    CK(c, c->s_out_re.ensure((size_t)3 * total * sizeof(double)));
+    double* o = c->s_out_re.as<double>();
+    CK(c, launch_measure(d_sum, d_diff, d_flags, d_rs, d_vs, d_k, k_rows, V, R, extra, r_times, v_times, n0, delta_r, delta_v, beam_pos,
+                         beam_step, fre_ind, ele_comp, ele_err, col_start, o, o + total, o + 2 * total, c->errflag.as<int>(), c->stream));
+    c->launches++;
+    CK(c, cudaMemcpyAsync(out_r, o, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(out_v, o + total, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(out_e, o + 2 * total, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return fetch_errflag(c, "motionParaMeasure: Index exceeds array bounds");
+}
+
 static int chunk_size(const rb200_ctx* c) {
     const char* env = getenv("RB200_CHUNK");
     int g = env ? atoi(env) : c->cfg.chunk_cpi;

@@ -51,6 +51,13 @@ cudaError_t launch_cfar1d_f64(const double* data, int rows, int cols, int ref, i
                               const int* rows_fix, int n_rows_fix, const int* cols_fix, int n_cols_fix,
                               uint8_t* out, int* err_flag, cudaStream_t st);
 
+// ---- post-CFAR measurement (measure_kernels.cu), all arrays column-major double on the device
+cudaError_t launch_flag_compaction(const double* flags, int V, int R, int* col_start, int* total, cudaStream_t st);
+cudaError_t launch_measure(const double* sum, const double* diff, const double* flags, const double* rScale, const double* vScale,
+                           const double* kValues, int kRows, int V, int R, int extra, int rTimes, int vTimes, int n0, double deltaR,
+                           double deltaV, double beamPosNum, double beamAngleStep, int freInd, double eleComp, double eleSysErr,
+                           const int* col_start, double* out_r, double* out_v, double* out_e, int* err_flag, cudaStream_t st);
+
 // ---- layout conversion (layout_kernels.cu): MATLAB column-major split double <-> device layouts
 cudaError_t launch_z_to_planar(const double* re, const double* im, float2* out, int rows, int cols, cudaStream_t st);          // out[row][col]
 cudaError_t launch_planar_to_z(const float2* in, double* re, double* im, int rows, int cols, cudaStream_t st);                // in[row][col]

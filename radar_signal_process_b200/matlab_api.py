@@ -119,6 +119,15 @@ def fun_MTD_produce_windows(echo_win, win_len=1536, win_size=4):
     return ctx.mtd_produce_windows(echo_win, win_len, starts, 8.0, 150)
 
 
+def motionParaMeasure(echo_MTD_sum_short, echo_MTD_diff_short, cfarResultFlag_Matrix_short, extraDots, rScale_short, deltaR,
+                      rInterpTimes, vScale, deltaV, vInterpTimes, kValues, beamPosNum, beamAngleStep, freInd, eleAngleComp,
+                      eleAngleSysErr, MTD_0_num):
+    """[rEstSeries, vEstSeries, eleAngleEstSeries] = motionParaMeasure(...)   CW/motionParaMeasure.m:1"""
+    return default_context().motion_para_measure(echo_MTD_sum_short, echo_MTD_diff_short, cfarResultFlag_Matrix_short, extraDots,
+                                                 rScale_short, deltaR, rInterpTimes, vScale, deltaV, vInterpTimes, kValues,
+                                                 beamPosNum, beamAngleStep, freInd, eleAngleComp, eleAngleSysErr, MTD_0_num)
+
+
 def executeCFAR(mtd, refCells_R, saveCells_R, T_CFAR_R, CFARmethod_R, refCells_V, saveCells_V, T_CFAR_V, CFARmethod_V,
                 MTD_0_num, rCFARDetect_Flag):
     return default_context().execute_cfar(mtd, refCells_R, saveCells_R, T_CFAR_R, CFARmethod_R, refCells_V, saveCells_V,

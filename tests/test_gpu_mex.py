@@ -99,3 +99,22 @@ def test_mex_executeCFAR_and_cfar1d_bit_identical():
     assert np.array_equal(Mex("Function_CFAR1D_sub")(d, 5, 7, 1.5, 1), mcode.Function_CFAR1D_sub(d, 5, 7, 1.5, 1))
     assert np.array_equal(Mex("Function_CFAR1D_sub_fixCells")(d, 5, 7, 1.5, 0, [1, 4], [2, 30, 59]),
                           mcode.Function_CFAR1D_sub_fixCells(d, 5, 7, 1.5, 0, [1, 4], [2, 30, 59]))
+
+
+def test_mex_motionParaMeasure():
+    rng = np.random.default_rng(6)
+    V, R, n0 = 48, 90, 2
+    s = rng.rayleigh(1.0, size=(V, R)) + 0.5
+    d = rng.normal(size=(V, R))
+    flags = np.zeros((V, R))
+    for v, r in ((10, 5), (30, 44), (n0 + 1, 0), (V - n0 - 1, R - 1)):
+        s[v, r] += 25
+        flags[v, r] = 1
+    rScale, vScale, kValues = 6.0 * np.arange(R), 0.3 * (24 - np.arange(V)), 10 + rng.random((11, 12))
+    args = (2, rScale, 6.0, 8, vScale, 0.3, 4, kValues, 3, 3.0, 1, 0.0, 0.0, n0)
+    rE, vE, eE = Mex("motionParaMeasure")(s, d, flags, *args, nargout=3)
+    wr, wv, we = mcode.motionParaMeasure(s, d, flags, *args)
+    assert rE.shape == (4, 1)
+    assert np.allclose(rE[:, 0], wr, rtol=1e-11) and np.allclose(vE[:, 0], wv, rtol=1e-11, atol=1e-12) and np.allclose(eE[:, 0], we, rtol=1e-11)
+    none = Mex("motionParaMeasure")(s, d, np.zeros((V, R)), *args)
+    assert none.size == 0

@@ -541,3 +541,32 @@ def test_sliding_window_reuse_matches_per_window_calls(lib):
         ctx.set_waveform(lib.waveforms.segments_mp(n, lib.waveforms.PULSE2, lib.waveforms.PULSE3))
         with pytest.raises(lib.MatlabIndexError):
             ctx.mtd_produce_windows(echo_win, win_len, [0, 2 * win_len - 10])
+
+
+def test_motionParaMeasure_matches_oracle(lib):
+    """post-CFAR measurement on the flagged cells (spline refinement + monopulse elevation)."""
+    rng = np.random.default_rng(51)
+    V, R, n0 = 64, 200, 3
+    s = rng.rayleigh(1.0, size=(V, R)) + 0.5
+    d = rng.normal(size=(V, R))
+    flags = np.zeros((V, R))
+    for _ in range(25):
+        v, r = int(rng.integers(n0 + 1, V - n0)), int(rng.integers(0, R))
+        s[max(v - 2, 0):v + 3, max(r - 2, 0):r + 3] += 30 * rng.random()
+        s[v, r] += 40
+        flags[v, r] = 1
+    flags[n0 + 1, 0] = flags[V - n0 - 1, R - 1] = flags[n0 + 2, 1] = 1            # edge windows on both axes
+    rScale = 6.0 * np.arange(R) + 100.0
+    vScale = 0.27 * (V // 2 - np.arange(V))
+    kValues = 10 + rng.random((11, 12))
+    for extra, rt, vt in ((2, 8, 4), (1, 5, 3), (4, 2, 2)):
+        args = (extra, rScale, 6.0, rt, vScale, 0.27, vt, kValues, 7, 3.0, 4, 0.3, -0.1, n0)
+        got = lib.motionParaMeasure(s, d, flags, *args)
+        want = mcode.motionParaMeasure(s, d, flags, *args)
+        assert len(got) == 3 and got[0].shape == want[0].shape == (int(flags.sum()),)
+        for g, w in zip(got, want):
+            assert np.allclose(g, w, rtol=1e-11, atol=1e-9)
+    empty = lib.motionParaMeasure(s, d, np.zeros((V, R)), *args)
+    assert all(e.shape == (0,) for e in empty)
+    with pytest.raises(lib.MatlabIndexError):
+        lib.motionParaMeasure(s, d, flags, 2, rScale, 6.0, 8, vScale, 0.27, 4, kValues, 12, 3.0, 4, 0, 0, n0)       # beamPosNum+1 > 12

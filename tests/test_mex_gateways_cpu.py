@@ -8,7 +8,7 @@ import pytest
 
 from mexharness import BUILD, Mex, MexError, ROOT
 
-NAMES = ["fun_MTD_produce", "fun_lss_pulse_compression", "fun_pulse_compression", "fun_Process_MTD", "fun_0v_pressing",
+NAMES = ["motionParaMeasure", "fun_MTD_produce", "fun_lss_pulse_compression", "fun_pulse_compression", "fun_Process_MTD", "fun_0v_pressing",
          "fun_0v_pressing_cw", "executeCFAR", "Function_CFAR1D_sub", "Function_CFAR1D_sub_fixCells"]
 
 
@@ -33,6 +33,7 @@ def test_gateway_loads_and_exports_mexfunction(name):
     ("executeCFAR", 10, "radar_b200:cfar:nargin"),
     ("Function_CFAR1D_sub", 4, "radar_b200:cfar1d:nargin"),
     ("Function_CFAR1D_sub_fixCells", 5, "radar_b200:cfar1d:nargin"),
+    ("motionParaMeasure", 16, "radar_b200:measure:nargin"),
 ])
 def test_wrong_nargin_raises_like_matlab(name, nargs, ident):
     with pytest.raises(MexError) as e:

@@ -258,3 +258,32 @@ def test_unpack_dbf24_known_words():
     assert mcode.dbf24_payload_size(4, 4)[2] == 8
     z4 = mcode.unpack_dbf24(np.zeros(sum(mcode.dbf24_payload_size(4, 4)[:2]), dtype=np.uint8), 4, 4)
     assert z4.shape == (4, 5)
+
+
+def test_motion_para_measure_oracle_known_answers():
+    # a separable Gaussian bump centred between cells: the spline arg-max lands on the nearest 1/times grid point
+    V, R = 40, 60
+    v0, r0 = 17.3, 31.6                      # 1-based fractional peak position
+    vv, rr = np.meshgrid(np.arange(1, V + 1), np.arange(1, R + 1), indexing="ij")
+    s = 100 * np.exp(-((vv - v0) ** 2) / 8.0 - ((rr - r0) ** 2) / 8.0)
+    d = 0.25 * s
+    flags = np.zeros((V, R))
+    flags[16, 31] = 1                        # cell (17, 32)
+    rScale = 6.0 * np.arange(R)
+    vScale = 0.5 * (20 - np.arange(V))
+    kValues = np.arange(1, 23, dtype=float).reshape(11, 2, order="F")
+    rE, vE, eE = mcode.motionParaMeasure(s, d, flags, 2, rScale, 6.0, 8, vScale, 0.5, 4, kValues, 1, 3.0, 2, 0.1, 0.2, 3)
+    assert rE.shape == (1,)
+    assert abs(rE[0] - (rScale[31] + (31.625 - 32) * 6.0)) < 1e-9          # nearest 1/8 to 31.6
+    assert abs(vE[0] - (vScale[16] - 0.25 * 0.5)) < 1e-9                   # nearest 1/4 to 17.3 is 17.25
+    assert abs(eE[0] - (1 * 3.0 + 2.5 - 0.25 * kValues[2, 1] + 0.1 + 0.2)) < 1e-12
+    # find() order is column-major and edges clamp the interpolation window
+    flags[:] = 0
+    flags[[4, 38, 10], [0, 59, 30]] = 1
+    rE, vE, eE = mcode.motionParaMeasure(s + 1, d, flags, 2, rScale, 6.0, 8, vScale, 0.5, 4, kValues, 0, 3.0, 0, 0, 0, 3)
+    assert rE.shape == (3,) and np.all(np.isfinite(rE)) and np.all(np.isfinite(vE))
+    # spline restatement: n = 5 not-a-knot reproduces a cubic exactly
+    x = np.arange(5.0)
+    y = 2 - x + 0.5 * x ** 2 - 0.1 * x ** 3
+    xq = np.linspace(0, 4, 33)
+    assert np.allclose(mcode.matlab_spline_eval(y, xq), 2 - xq + 0.5 * xq ** 2 - 0.1 * xq ** 3, atol=1e-12)
