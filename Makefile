@@ -6,7 +6,7 @@ CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libradar_b200.so
 NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas --expt-relaxed-constexpr
 CU_SRCS   := $(CSRC)/api.cu $(CSRC)/pc_kernels.cu $(CSRC)/mtd_kernels.cu $(CSRC)/mtd64_kernel.cu $(CSRC)/chain64_kernel.cu $(CSRC)/dbf_kernel.cu $(CSRC)/measure_kernels.cu $(CSRC)/cfar_kernels.cu $(CSRC)/layout_kernels.cu
-CU_OBJS   := $(CU_SRCS:.cu=.o)
+CU_OBJS   := $(CU_SRCS:.cu=.o) $(CSRC)/reader.o
 HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/radar_b200.h
 
 MEXDIR    := mex
@@ -33,6 +33,9 @@ $(MEXBUILD)/fun_0v_pressing_cw.so: $(MEXDIR)/fun_0v_pressing.cpp $(MEXDIR)/rb200
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) $(EXTRA_NVFLAGS) -c $< -o $@
+
+$(CSRC)/reader.o: $(CSRC)/reader.cpp include/radar_b200.h
+	$(CXX) -O2 -std=c++17 -fPIC -Wall -c $< -o $@
 
 $(LIB): $(CU_OBJS)
 	$(NVCC) -shared -o $@ $(CU_OBJS) -gencode arch=compute_100a,code=sm_100a -cudart shared

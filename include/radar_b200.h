@@ -217,6 +217,23 @@ int rb200_get_stage_ms(rb200_ctx* ctx, float ms[3], int* n_chunks, int* n_cpis);
  * (rdm_out [cpi][beam][v][range], rb200_det.lane) is a beam index and buffers are sized with n_beams.   */
 int rb200_set_dbf(rb200_ctx* ctx, const double* w_re, const double* w_im, int n_beams);
 
+/* f2: capture-file byte stream + per-PRT frame parser (host code, no GPU needed).
+ * Replaces read_continuous_file_stream.m:22 (files <dir>/1.00000N.bin, DataFullPathGen.m:10-16, one logical stream
+ * with the reference's file-index behaviour) and the DDC branch of FrameDataRead_xzr.m:57-198.
+ * rb200_reader_next_frame_ddc parses up to n_prt PRTs (64 B head | 128 B realtime | payload padded to 64 B | 64 B
+ * tail) and stores their int16 payloads as [prt][range][channel][I,Q] in raw_out (typically pinned memory handed
+ * straight to rb200_chain_i16).  *prts_read < n_prt with *end_of_stream = 1 when the stream ends or a PRT is
+ * inconsistent (the M-code's "frame not completed").  Optional per-PRT header fields: frame number (head word 1),
+ * servo angle (low 16 bits of word 5, 0.1 deg), 64-bit timer (words 9-10).                                        */
+typedef struct rb200_reader rb200_reader;
+int rb200_reader_open(rb200_reader** out, const char* dir);
+int rb200_reader_close(rb200_reader* r);
+const char* rb200_reader_last_error(const rb200_reader* r);
+int rb200_reader_state(const rb200_reader* r, int* file_index, long long* pos);
+int rb200_reader_next_frame_ddc(rb200_reader* r, int n_prt, int n_range, int n_channels, int16_t* raw_out,
+                                uint32_t* frame_no, uint16_t* servo_angle, uint64_t* timer_cnt,
+                                int* prts_read, int* end_of_stream);
+
 /* f3: [rEst, vEst, eleEst] = motionParaMeasure(sum, diff, flags, extraDots, rScale, deltaR, rInterpTimes, vScale, deltaV,
  *          vInterpTimes, kValues, beamPosNum, beamAngleStep, freInd, eleAngleComp, eleAngleSysErr, MTD_0_num)
  * Replaces CW/motionParaMeasure.m:1.  sum / diff / flags: V x R column-major double; r_scale: R values; v_scale: V

@@ -560,3 +560,102 @@ def motionParaMeasure(mtd_sum, mtd_diff, flags, extraDots, rScale, deltaR, rInte
         vEst.append(v_est)
         eEst.append(e_est)
     return np.array(rEst), np.array(vEst), np.array(eEst)
+
+
+# ----------------------------------------------------------------------------------------------
+# f2  read_continuous_file_stream.m:22-168 + DDC branch of FrameDataRead_xzr.m:57-198 (TEST ORACLE)
+# ----------------------------------------------------------------------------------------------
+class ContinuousFileStream:
+    """The persistent state machine of read_continuous_file_stream.m, file names per DataFullPathGen.m:10-16."""
+
+    def __init__(self, directory):
+        self.dir = directory
+        self.is_open = False
+        self.data = b""
+        self.pos = 0
+        self.max_len = 0
+        self.index = 0                                                     # :43
+
+    def _name(self, i):
+        name = "1.00000%d.bin" % i if i < 10 else ("1.0000%d.bin" % i if i < 100 else "1.000%d.bin" % i)
+        return os.path.join(self.dir, name)
+
+    def _open(self, i):
+        try:
+            self.data = open(self._name(i), "rb").read()
+        except OSError:
+            return False
+        self.max_len, self.pos, self.is_open = len(self.data), 0, True
+        return True
+
+    def read(self, want):
+        """-> (bytes, actual_len, is_end_of_stream)"""
+        if not self.is_open:
+            self.index += 1                                                # :48
+            if not self._open(self.index):
+                self.is_open = False
+                return b"", 0, True                                        # :55-59
+        eos = False
+        if self.pos + want > self.max_len:                                 # :85
+            out = self.data[self.pos:self.max_len]
+            self.is_open = False
+            remain = want - len(out)
+            if remain > 0:
+                self.index += 1                                            # :101
+                if not self._open(self.index):
+                    self.pos, self.max_len = 0, 0
+                    return out, len(out), True                             # :106-113
+                part2 = self.data[:remain]
+                out += part2
+                self.pos += len(part2)                                     # :133
+        elif self.pos + want == self.max_len:                              # :137
+            out = self.data[self.pos:self.pos + want]
+            self.is_open = False
+            self.index += 1                                                # :148 (then :48 increments again)
+            self.pos, self.max_len = 0, 0
+        else:
+            out = self.data[self.pos:self.pos + want]
+            self.pos += len(out)
+        if len(out) < want and self.is_open:
+            eos = True                                                     # :160-163
+        return out, len(out), eos
+
+
+def frame_data_read_ddc(stream, prtNum, point_PRT, channel_num):
+    """DDC branch of FrameDataRead_xzr.m:57-198 without the DBF product: returns (sig[prt, range, channel] complex,
+    servo_angle, frame_no, timer_cnt, prts_read, stream_end)."""
+    sig = np.zeros((prtNum, point_PRT, channel_num), dtype=np.complex128)
+    servo = np.zeros(prtNum)
+    frame_no = np.zeros(prtNum, dtype=np.uint64)
+    timer = np.zeros(prtNum, dtype=np.uint64)
+    cur = 0
+    while cur < prtNum:                                                    # :57
+        hb, n, eos = stream.read(64)                                       # :62
+        if eos or n < 64:
+            return sig, servo, frame_no, timer, cur, True
+        h = np.frombuffer(hb, dtype="<u4")                                 # :70
+        ch = int(h[3]) % 256                                               # :77
+        pulse_data_num = int(h[6])                                         # :79
+        data_type = int(h[7]) % 256                                        # :80
+        if pulse_data_num <= 0:
+            return sig, servo, frame_no, timer, cur, True                  # :90-94
+        _, n, eos = stream.read(128)                                       # :97
+        if eos or n < 128:
+            return sig, servo, frame_no, timer, cur, True
+        assert data_type == 1
+        size, pad = ddc_payload_size(pulse_data_num, ch)                   # :109,115-119
+        pb, n, eos = stream.read(size + pad)                               # :122
+        if eos or n < size + pad:
+            return sig, servo, frame_no, timer, cur, True
+        x = unpack_ddc_i16(np.frombuffer(pb, dtype=np.uint8), pulse_data_num, ch)     # :138,150-156
+        if x.shape != (point_PRT, channel_num):                            # :171-176
+            return sig, servo, frame_no, timer, cur, True
+        sig[cur] = x                                                       # :179-180
+        servo[cur] = int(h[4]) % 65536                                     # :78,181
+        frame_no[cur] = int(h[0])                                          # :74
+        timer[cur] = int(h[8]) + int(h[9]) * 2 ** 32                       # :83
+        cur += 1
+        _, n, eos = stream.read(64)                                        # :184
+        if eos or n < 64:
+            return sig, servo, frame_no, timer, cur, True
+    return sig, servo, frame_no, timer, cur, False

@@ -62,7 +62,8 @@ EXPORTS = [
     "rb200_process_mtd_z", "rb200_zero_v_pressing_d", "rb200_mtd_produce_z", "rb200_cfar1d_sub_d",
     "rb200_cfar1d_fix_d", "rb200_execute_cfar_d", "rb200_unpack_ddc_i16", "rb200_chain_i16",
     "rb200_chain_enqueue", "rb200_chain_fetch", "rb200_debug_fetch_pc", "rb200_last_device_ms",
-    "rb200_last_launch_count", "rb200_set_dbf", "rb200_set_stage_timing", "rb200_get_stage_ms", "rb200_unpack_dbf24", "rb200_mtd_produce_windows_z", "rb200_motion_para_measure_d",
+    "rb200_last_launch_count", "rb200_set_dbf", "rb200_set_stage_timing", "rb200_get_stage_ms", "rb200_unpack_dbf24", "rb200_mtd_produce_windows_z", "rb200_motion_para_measure_d", "rb200_reader_open", "rb200_reader_close",
+    "rb200_reader_last_error", "rb200_reader_state", "rb200_reader_next_frame_ddc",
 ]
 
 _lib = None
@@ -112,6 +113,12 @@ def load():
     lib.rb200_motion_para_measure_d.argtypes = [vp, dp, dp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_double, C.c_int, dp, C.c_double, C.c_int,
                                                 dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
                                                 dp, dp, dp, C.c_int, C.POINTER(C.c_int)]
+    lib.rb200_reader_open.argtypes = [C.POINTER(vp), C.c_char_p]
+    lib.rb200_reader_close.argtypes = [vp]
+    lib.rb200_reader_last_error.argtypes = [vp]
+    lib.rb200_reader_last_error.restype = C.c_char_p
+    lib.rb200_reader_state.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
+    lib.rb200_reader_next_frame_ddc.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

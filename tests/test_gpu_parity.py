@@ -570,3 +570,28 @@ def test_motionParaMeasure_matches_oracle(lib):
     assert all(e.shape == (0,) for e in empty)
     with pytest.raises(lib.MatlabIndexError):
         lib.motionParaMeasure(s, d, flags, 2, rScale, 6.0, 8, vScale, 0.27, 4, kValues, 12, 3.0, 4, 0, 0, n0)       # beamPosNum+1 > 12
+
+
+def test_capture_files_to_detections_end_to_end(lib, tmp_path):
+    """f2 + the hot path: framed capture files -> C++ reader -> (host buffer) -> rb200_chain_i16 -> detections, against
+    the oracle's frame parser + chain on the same bytes."""
+    from radar_signal_process_b200.reader import FrameReader
+    P, R, C, B = 64, 512, 4, 2
+    raw, _ = synth.s3_batch(B, P=P, R=R, C=C, n_targets=2, r_lo=40, r_hi=R - 100)
+    blob = b"".join(synth.frame_prt(raw[b, p], frame_no=b, prt_no=p, channel_num=C) for b in range(B) for p in range(P))
+    cut = len(blob) // 3 + 17
+    (tmp_path / "1.000001.bin").write_bytes(blob[:cut])
+    (tmp_path / "1.000002.bin").write_bytes(blob[cut:])
+    rd = FrameReader(tmp_path)
+    batch = np.zeros((B, P, R, C, 2), dtype=np.int16)
+    for b in range(B):
+        _, meta, nread, eos = rd.next_frame(P, R, C, out=batch[b])
+        assert nread == P and not eos and np.all(meta["frame_no"] == b)
+    assert np.array_equal(batch, raw)
+    ref = mcode.load_ref("refDDCDataMF1")
+    cfar = synth.cfar_tuple(synth.S3_CFAR)
+    out = vec.chain(batch, B, P, R, C, ("single", ref), cfar, near_tol=RTOL)
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar) as ctx:
+        rdm, dets, n = ctx.chain(batch, B)
+    _close(rdm, out["rdm"])
+    _compare_flags(dets, out, B, C, P, R, lib)
