@@ -461,8 +461,17 @@ static int zero_v_rows(int P, int div, int* lo, int* hi) {
     return RB200_OK;
 }
 
+struct FusedV {            // optional velocity-CFAR fusion into the shared-memory MTD kernels
+    const CfarParams* cf;
+    float t_v;
+    void* dets;
+    int* det_count;
+    uint32_t* vmask;
+    int* err_flag;
+};
+
 static int run_mtd(rb200_ctx* ctx, const float2* in, float* out, int P, int in_ld, int out_ld, int cols, int n_slabs,
-                   double beta, int zero_div, int mti_lag, cudaStream_t st) {
+                   double beta, int zero_div, int mti_lag, cudaStream_t st, const FusedV* fv = nullptr) {
     if (P < 1) return fail(ctx, RB200_ERR_ARG, "MTD: P < 1");
     if (!mtd_has_fast_path(P) && P > mtd_generic_max_p()) return fail(ctx, RB200_ERR_UNSUPPORTED, "MTD: P beyond the generic kernel's shared-memory envelope (12288)");
     MtdPlan* mp = nullptr;
@@ -483,6 +492,15 @@ static int run_mtd(rb200_ctx* ctx, const float2* in, float* out, int P, int in_l
     if (rc) return fail(ctx, rc, "fun_0v_pressing: Index in position 1 is invalid");
     p.n_stages = mp->n_stages;
     for (int i = 0; i < mp->n_stages; ++i) p.radix[i] = mp->radix[i];
+    if (fv) {
+        p.cfar_on = 1;
+        p.cf = *fv->cf;
+        p.t_v = fv->t_v;
+        p.dets = fv->dets;
+        p.det_count = fv->det_count;
+        p.vmask = fv->vmask;
+        p.err_flag = fv->err_flag;
+    }
     CK(ctx, launch_mtd(p, n_slabs, st));
     ctx->launches++;
     return RB200_OK;
@@ -1269,16 +1287,26 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
                                   c->counters.as<int>(), sl.colmask.as<unsigned long long>(), R, c->errflag.as<int>(), c->n_sms, cs));
             c->launches++;
         } else {
-            rc = run_mtd(c, pc_buf, rdm_chunk, P, R, R, R, g * C, k.kaiser_beta, k.zero_v_div, k.mti_lag, cs);
+            // hits of this chunk start where the list currently ends
+            if (cp.v_hi > cp.v_lo)
+                CK(c, cudaMemcpyAsync(c->counters.as<int>() + 2, c->counters.as<int>() + 0, sizeof(int), cudaMemcpyDeviceToDevice, cs));
+            const bool fuse_v = cp.v_hi > cp.v_lo && mtd_fast_fuses_cfar(P) && (cp.v_hi - cp.v_lo) >= 2 * (cp.ref_v + cp.guard_v) &&
+                                !getenv("RB200_NO_FUSED_V");
+            FusedV fvp = {&cp, (float)k.cfar_t_v, c->dets_v.p, c->counters.as<int>() + 0, c->vmask.as<uint32_t>(), c->errflag.as<int>()};
+            rc = run_mtd(c, pc_buf, rdm_chunk, P, R, R, R, g * C, k.kaiser_beta, k.zero_v_div, k.mti_lag, cs, fuse_v ? &fvp : nullptr);
             if (rc) return rc;
             if (timed) stage_event(c, cs);
             if (cp.v_hi > cp.v_lo) {
-                // hits of this chunk start where the list currently ends
-                CK(c, cudaMemcpyAsync(c->counters.as<int>() + 2, c->counters.as<int>() + 0, sizeof(int), cudaMemcpyDeviceToDevice, cs));
-                CK(c, launch_cfar_f32(rdm_chunk, cp, (float)k.cfar_t_r, (float)k.cfar_t_v, g * C, c->dets_v.p, c->counters.as<int>() + 0,
-                                      c->dets_2d.p, c->counters.as<int>() + 1, c->vmask.as<uint32_t>(), nullptr, nullptr,
-                                      c->errflag.as<int>(), cs));
-                c->launches += cp.range_stage ? 2 : 1;
+                if (fuse_v) {
+                    CK(c, launch_cfar_r_f32(rdm_chunk, cp, (float)k.cfar_t_r, c->dets_v.p, c->counters.as<int>() + 0, c->dets_2d.p,
+                                            c->counters.as<int>() + 1, c->vmask.as<uint32_t>(), c->errflag.as<int>(), cs));
+                    c->launches += cp.range_stage ? 1 : 0;
+                } else {
+                    CK(c, launch_cfar_f32(rdm_chunk, cp, (float)k.cfar_t_r, (float)k.cfar_t_v, g * C, c->dets_v.p, c->counters.as<int>() + 0,
+                                          c->dets_2d.p, c->counters.as<int>() + 1, c->vmask.as<uint32_t>(), nullptr, nullptr,
+                                          c->errflag.as<int>(), cs));
+                    c->launches += cp.range_stage ? 2 : 1;
+                }
             }
         }
         if (rdm_host)

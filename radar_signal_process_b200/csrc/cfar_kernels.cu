@@ -20,32 +20,11 @@
 // bit-identical to the double-precision M-code).
 #include "common.cuh"
 #include "kernels.h"
+#include "cfar_core.cuh"
 #include "../../include/radar_b200.h"
 #include <cstdlib>
 
 namespace rb {
-
-// One CA-CFAR decision for element y of an axis of length N whose element i sits at base[i*stride].
-template <typename T>
-__device__ __forceinline__ bool cfar_decide(const T* __restrict__ base, ptrdiff_t stride, int y, int N, int ref, int guard,
-                                            T thr, int method, int* err_flag) {
-    const int l1 = y - guard - ref;
-    const int r1 = y + guard + 1;
-    const bool okL = l1 >= 0;
-    const bool okR = (y + guard + ref) <= N - 1;
-    if (!okL && !okR) {            // MATLAB: index exceeds array bounds
-        if (err_flag) *err_flag = 1;
-        return false;
-    }
-    T sl = 0, sr = 0;
-    if (okL) for (int j = 0; j < ref; ++j) sl += base[(ptrdiff_t)(l1 + j) * stride];
-    if (okR) for (int j = 0; j < ref; ++j) sr += base[(ptrdiff_t)(r1 + j) * stride];
-    const T mr = sr / (T)ref, ml = sl / (T)ref;
-    const T a = okL ? ml : mr;
-    const T b = okR ? mr : ml;
-    const T mu = method == 0 ? (a > b ? a : b) : (a < b ? a : b);
-    return base[(ptrdiff_t)y * stride] >= mu * thr;
-}
 
 // Stage V.  One thread walks down one range column (rows [v_lo, v_hi), split over blockIdx.z into row
 // segments): consecutive rows re-use 9 of the 10 reference rows from L1, every global access is a
@@ -270,6 +249,15 @@ static cudaError_t run_cfar(const T* rdm, const CfarParams& p, T t_r, T t_v, int
 cudaError_t launch_cfar_f32(const float* rdm, const CfarParams& p, float t_r, float t_v, int n_slabs, void* dets_v, int* count_v,
                             void* dets_2d, int* count_2d, uint32_t* vmask, uint8_t* flag2d, uint8_t* flagv, int* err_flag, cudaStream_t st) {
     return run_cfar<float, true>(rdm, p, t_r, t_v, n_slabs, (rb200_det*)dets_v, count_v, (rb200_det*)dets_2d, count_2d, vmask, flag2d, flagv, err_flag, st);
+}
+
+// range stage only (velocity hits already in dets_v / vmask, e.g. produced by the fused mtd_fast_kernel)
+cudaError_t launch_cfar_r_f32(const float* rdm, const CfarParams& p, float t_r, void* dets_v, int* count_v, void* dets_2d, int* count_2d,
+                              uint32_t* vmask, int* err_flag, cudaStream_t st) {
+    if (!p.range_stage) return cudaSuccess;
+    cfar_r_kernel<float, true><<<(p.max_det + 127) / 128, 128, 0, st>>>(rdm, p, t_r, (rb200_det*)dets_v, count_v, (rb200_det*)dets_2d, count_2d,
+                                                                        vmask, nullptr, err_flag);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_cfar_f64_colmajor(const double* rdm, const CfarParams& p, double t_r, double t_v, void* dets_v, int* count_v,

@@ -49,6 +49,17 @@ struct PcParams {
     int n_lines;            // planar: number of lines
 };
 
+struct CfarParams {
+    int V, R;               // full RDM size
+    int v_lo, v_hi;         // 0-based tested rows [v_lo, v_hi)  (n0+1 .. V-n0)
+    int ref_r, guard_r, meth_r;
+    int ref_v, guard_v, meth_v;
+    int range_stage;
+    int max_det;
+    int n_lanes;            // slabs per CPI (detection record: cpi = slab / n_lanes, lane = slab % n_lanes)
+    int cpi0;               // CPI index of slab 0 (chunked batches)
+};
+
 struct MtdParams {
     const float2* in;       // planar [slab][prt][range]
     float* out;             // [slab][v][range]
@@ -62,6 +73,15 @@ struct MtdParams {
     // generic Stockham only
     int n_stages;
     int radix[16];
+    // optional fused velocity-axis CFAR (mtd_fast_kernel only): magnitudes of the CTA's tile are kept in shared
+    // memory and every thread decides R consecutive rows of its column; hits go to dets / vmask like cfar_v_kernel
+    int cfar_on;
+    CfarParams cf;
+    float t_v;
+    void* dets;
+    int* det_count;
+    uint32_t* vmask;
+    int* err_flag;
 };
 
 struct rb200_det_fwd;
@@ -99,15 +119,5 @@ struct Chain64Params {
     int* err_flag;
 };
 
-struct CfarParams {
-    int V, R;               // full RDM size
-    int v_lo, v_hi;         // 0-based tested rows [v_lo, v_hi)  (n0+1 .. V-n0)
-    int ref_r, guard_r, meth_r;
-    int ref_v, guard_v, meth_v;
-    int range_stage;
-    int max_det;
-    int n_lanes;            // slabs per CPI (detection record: cpi = slab / n_lanes, lane = slab % n_lanes)
-    int cpi0;               // CPI index of slab 0 (chunked batches)
-};
 
 }  // namespace rb

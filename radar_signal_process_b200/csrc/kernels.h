@@ -25,6 +25,7 @@ cudaError_t launch_unpack_dbf24(const uint8_t* bytes, float2* out, int n_prt, in
 
 // ---- K2 MTD (mtd_kernels.cu)
 bool mtd_has_fast_path(int P);
+bool mtd_fast_fuses_cfar(int P);          // the P = R*R shared-memory kernels can run the velocity CFAR on their tile
 cudaError_t launch_mtd(const MtdParams& p, int n_slabs, cudaStream_t st);
 int mtd_generic_max_p();
 
@@ -43,6 +44,8 @@ cudaError_t launch_chain64(const Chain64Params& q, int n_sms, cudaStream_t st);
 // chain variant: float RDM [slab][V][R] row-major -> velocity-hit list + 2-D list (+ optional dense uint8 flags)
 cudaError_t launch_cfar_f32(const float* rdm, const CfarParams& p, float t_r, float t_v, int n_slabs, void* dets_v, int* count_v,
                             void* dets_2d, int* count_2d, uint32_t* vmask, uint8_t* flag2d, uint8_t* flagv, int* err_flag, cudaStream_t st);
+cudaError_t launch_cfar_r_f32(const float* rdm, const CfarParams& p, float t_r, void* dets_v, int* count_v, void* dets_2d, int* count_2d,
+                              uint32_t* vmask, int* err_flag, cudaStream_t st);
 // MATLAB variant: one double V x R column-major matrix -> dense uint8 flags (column-major)
 cudaError_t launch_cfar_f64_colmajor(const double* rdm, const CfarParams& p, double t_r, double t_v, void* dets_v, int* count_v,
                                      uint32_t* vmask, uint8_t* flag2d, uint8_t* flagv, int* err_flag, cudaStream_t st);

@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "radix.cuh"
 #include "kernels.h"
+#include "cfar_core.cuh"
+#include "../../include/radar_b200.h"
 
 namespace rb {
 
@@ -31,8 +33,16 @@ __device__ __forceinline__ float2 mtd_load(const float2* __restrict__ col, int p
     return make_float2(a.x - b.x, a.y - b.y);
 }
 
-template <int R, int TR>
-__global__ void __launch_bounds__(TR * R)
+__device__ __forceinline__ float mtd_fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // <= 2 ulp; the parity bar is 1e-4 relative
+    return r;
+}
+
+// CF: 0 = no CFAR, 1 = fused velocity CFAR with run-time (ref, guard), 2 = fused with the reference's default
+// protection/reference cells (5 reference, 7 guard: CW/main_cfar.m:147-154) as compile-time constants.
+template <int R, int TR, bool MTI, int CF>
+__global__ void __launch_bounds__(TR * R, 2)
 mtd_fast_kernel(const MtdParams p) {
     constexpr int P = R * R;
     extern __shared__ float2 sm[];   // [P][TR]
@@ -41,15 +51,28 @@ mtd_fast_kernel(const MtdParams p) {
     const int slab = blockIdx.y;
     const int r = blockIdx.x * TR + rl;
     const bool ok = r < p.cols;
-    const float2* col = p.in + (size_t)slab * P * p.in_ld + r;
+    // 32-bit element offsets inside one slab (P * in_ld < 2^31 is checked by the launcher)
+    const float2* col = p.in + (size_t)slab * P * p.in_ld + (ok ? r : 0) + u * p.in_ld;
+    const int step = R * p.in_ld;
 
     float2 v[R];
+    if (MTI) {
+        // x[p + lag] - x[p], the last `lag` pulses are zero (MP/fun_Process_MTI.m:20-22)
+        const int lag_off = p.mti_lag * p.in_ld;
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-        const int prt = u + j * R;
-        float2 x = make_float2(0.f, 0.f);
-        if (ok) x = mtd_load(col, prt, P, p.in_ld, p.mti_lag);
-        v[j] = cscale(x, __ldg(p.window + prt));
+        for (int j = 0; j < R; ++j) {
+            const int prt = u + j * R;
+            float2 x = make_float2(0.f, 0.f);
+            if (prt < P - p.mti_lag) {
+                const float2 a = __ldg(col + j * step + lag_off);
+                const float2 b = __ldg(col + j * step);
+                x = make_float2(a.x - b.x, a.y - b.y);
+            }
+            v[j] = cscale(x, __ldg(p.window + prt));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = cscale(__ldg(col + j * step), __ldg(p.window + u + j * R));
     }
     Dft<R, -1>::run(v);
 #pragma unroll
@@ -60,15 +83,114 @@ mtd_fast_kernel(const MtdParams p) {
 #pragma unroll
     for (int j = 0; j < R; ++j) v[j] = sm[(u * R + j) * TR + rl];
     Dft<R, -1>::run(v);
-    if (ok) {
+    if (CF == 0) {
+        if (!ok) return;
         float* out = p.out + (size_t)slab * P * p.out_ld + r;
 #pragma unroll
         for (int k1 = 0; k1 < R; ++k1) {
-            const int m = u + R * k1;                  // Doppler bin
-            const int row = (m + P / 2) & (P - 1);     // fftshift
-            float mag = sqrtf(v[k1].x * v[k1].x + v[k1].y * v[k1].y);
+            const int row = (u + R * k1 + P / 2) & (P - 1);     // Doppler bin u + R*k1 after fftshift
+            float mag = mtd_fast_sqrt(v[k1].x * v[k1].x + v[k1].y * v[k1].y);
             if (row >= p.zv_lo && row <= p.zv_hi) mag = 0.f;
-            out[(size_t)row * p.out_ld] = mag;
+            out[row * p.out_ld] = mag;
+        }
+        return;
+    }
+    // The magnitude tile [P][TR] re-uses the exchange buffer (2*P*TR floats) once everybody has read it; it sits
+    // P/2 rows into the buffer so that window reads up to P/2 rows outside the tile stay inside the allocation
+    // (those values are never used: the edge rule replaces the side that does not fit).
+    float* mag_sm = reinterpret_cast<float*>(sm) + (P / 2) * TR;
+    __syncthreads();
+    {
+        float* out = p.out + (size_t)slab * P * p.out_ld + r;
+#pragma unroll
+        for (int k1 = 0; k1 < R; ++k1) {
+            const int row = (u + R * k1 + P / 2) & (P - 1);
+            float mag = mtd_fast_sqrt(v[k1].x * v[k1].x + v[k1].y * v[k1].y);
+            if (row >= p.zv_lo && row <= p.zv_hi) mag = 0.f;
+            if (ok) out[row * p.out_ld] = mag;
+            mag_sm[row * TR + rl] = mag;
+        }
+    }
+    // ---- fused velocity-axis CA-CFAR (CW/executeCFAR.m:28, CW/Function_CFAR1D_sub.m:17-69) on the tile ----
+    // Thread (u, rl) decides rows [u*R, (u+1)*R) of column rl; the reference windows come from shared memory.
+    __syncthreads();
+    const int nv = p.cf.v_hi - p.cf.v_lo;
+    const int ref = CF == 2 ? 5 : p.cf.ref_v;
+    const int guard = CF == 2 ? 7 : p.cf.guard_v;
+    const int H = ref + guard;
+    const int y0 = u * R - p.cf.v_lo;                  // axis position of this thread's first row (may be negative)
+    const float* mcol = mag_sm + p.cf.v_lo * TR + rl;  // mcol[y*TR] = x[v_lo + y][r]
+    float ml[R], mr[R], xc[R];
+    if (CF == 2) {
+        constexpr int HH = 12, W = R + 2 * HH;
+        float w[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) w[k] = mcol[(y0 - HH + k) * TR];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            ml[i] = ((((w[i] + w[i + 1]) + w[i + 2]) + w[i + 3]) + w[i + 4]);
+            mr[i] = ((((w[i + 20] + w[i + 21]) + w[i + 22]) + w[i + 23]) + w[i + 24]);
+            xc[i] = w[i + HH];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            ml[i] = 0.f;
+            mr[i] = 0.f;
+            xc[i] = mcol[(y0 + i) * TR];
+        }
+        const float* pl = mcol + (y0 - H) * TR;
+        const float* pr = mcol + (y0 + guard + 1) * TR;
+#pragma unroll 1
+        for (int j = 0; j < ref; ++j) {                // R independent accumulations per side in flight
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                ml[i] += pl[i * TR];
+                mr[i] += pr[i * TR];
+            }
+            pl += TR;
+            pr += TR;
+        }
+    }
+    const float inv_ref = 1.f / (float)ref;
+    const int Rw = (p.cf.R + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    uint32_t* vm = p.vmask + ((size_t)slab * p.cf.V + u * R) * Rw + (r >> 5);   // a warp covers 32 consecutive columns
+    const bool vm_ok = lane == 0 && (r >> 5) < Rw;
+    const uint32_t det_hdr = (uint32_t)(slab % p.cf.n_lanes) << 16 |
+                             (uint32_t)(p.cf.range_stage ? RB200_DET_V : (RB200_DET_V | RB200_DET_2D)) << 24;
+    const uint32_t det_cpi = (uint32_t)(p.cf.cpi0 + slab / p.cf.n_lanes);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int y = y0 + i;
+        if (y < 0 || y >= nv) continue;                // warp-uniform: u is warp-uniform for TR >= 32
+        const bool okL = y - H >= 0;
+        const bool okR = y + H <= nv - 1;
+        if (!okL && !okR) {                            // MATLAB: index exceeds array bounds
+            if (threadIdx.x == 0) *p.err_flag = 1;
+            continue;
+        }
+        const float a = (okL ? ml[i] : mr[i]) * inv_ref;
+        const float b = (okR ? mr[i] : ml[i]) * inv_ref;
+        const float mu = p.cf.meth_v == 0 ? fmaxf(a, b) : fminf(a, b);
+        const bool hit = ok && xc[i] >= mu * p.t_v;
+        const unsigned ball = __ballot_sync(0xffffffffu, hit);
+        if (vm_ok) vm[i * Rw] = ball;
+        if (ball == 0) continue;
+        int basei = 0;
+        if (lane == 0) basei = atomicAdd(p.det_count, __popc(ball));
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        if (hit) {
+            const int slot = basei + __popc(ball & ((1u << lane) - 1u));
+            if (slot < p.cf.max_det) {
+                // rb200_det {u32 cpi, u32 r, u16 v, u8 lane, u8 kind, f32 amp} written as one 16-byte store
+                uint4 d;
+                d.x = det_cpi;
+                d.y = (uint32_t)r;
+                d.z = (uint32_t)(u * R + i) | det_hdr;
+                d.w = __float_as_uint(xc[i]);
+                reinterpret_cast<uint4*>(p.dets)[slot] = d;
+            }
         }
     }
 }
@@ -131,18 +253,31 @@ __global__ void mtd_generic_kernel(const MtdParams p) {
 }
 
 bool mtd_has_fast_path(int P) { return P == 64 || P == 256; }
+bool mtd_fast_fuses_cfar(int P) { return P == 64 || P == 256; }
 int mtd_generic_max_p() { return 12288; }
 
 template <int R, int TR>
 static cudaError_t launch_fast(const MtdParams& p, int n_slabs, cudaStream_t st) {
     constexpr int P = R * R;
     const size_t smem = (size_t)P * TR * sizeof(float2);
-    static size_t configured[64] = {};
-    cudaError_t ce = ensure_dynamic_smem(mtd_fast_kernel<R, TR>, smem, configured);
-    if (ce != cudaSuccess) return ce;
     dim3 grid((p.cols + TR - 1) / TR, n_slabs, 1);
     if (n_slabs > 65535) return cudaErrorInvalidConfiguration;
-    mtd_fast_kernel<R, TR><<<grid, TR * R, smem, st>>>(p);
+    if ((size_t)P * p.in_ld >= (1ull << 31) || (size_t)P * p.out_ld >= (1ull << 31)) return cudaErrorInvalidValue;
+    const int cf = !p.cfar_on ? 0 : (p.cf.ref_v == 5 && p.cf.guard_v == 7) ? 2 : 1;
+    if (p.cfar_on && 2 * (p.cf.ref_v + p.cf.guard_v) > P) return cudaErrorInvalidValue;   // window reads stay inside the buffer
+#define RB_MTD_FAST(MTI, CF)                                                                                   \
+    do {                                                                                                       \
+        static size_t configured[64] = {};                                                                     \
+        cudaError_t ce = ensure_dynamic_smem(mtd_fast_kernel<R, TR, MTI, CF>, smem, configured);               \
+        if (ce != cudaSuccess) return ce;                                                                      \
+        mtd_fast_kernel<R, TR, MTI, CF><<<grid, TR * R, smem, st>>>(p);                                        \
+    } while (0)
+    if (p.mti_lag > 0) {
+        if (cf == 0) RB_MTD_FAST(true, 0); else if (cf == 1) RB_MTD_FAST(true, 1); else RB_MTD_FAST(true, 2);
+    } else {
+        if (cf == 0) RB_MTD_FAST(false, 0); else if (cf == 1) RB_MTD_FAST(false, 1); else RB_MTD_FAST(false, 2);
+    }
+#undef RB_MTD_FAST
     return cudaGetLastError();
 }
 

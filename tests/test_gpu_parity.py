@@ -372,6 +372,9 @@ def test_chain_detection_overflow_is_reported(lib):
     dict(P=64, R=512, C=2, B=1, cfar=(5, 7, 5.0, 0, 5, 7, 5.0, 0, 0, 1), mti=30, zdiv=150, chunk=1),    # MTI on P=64 -> shared-memory MTD path
     dict(P=128, R=384, C=2, B=1, cfar=(5, 7, 5.0, 0, 5, 7, 5.0, 0, 1, 1), mti=0, zdiv=150, chunk=1),    # generic Stockham Doppler length
     dict(P=48, R=300, C=2, B=2, cfar=(5, 7, 5.0, 0, 4, 3, 5.0, 0, 0, 1), mti=0, zdiv=0, chunk=2),       # P = 2^4*3, no zero-velocity mask
+    dict(P=256, R=333, C=2, B=2, cfar=(4, 2, 5.0, 1, 6, 3, 5.0, 1, 3, 1), mti=0, zdiv=150, chunk=1),    # P=256 fused V-CFAR, run-time windows, SO, ragged R
+    dict(P=256, R=288, C=1, B=1, cfar=(5, 7, 6.0, 0, 5, 7, 6.0, 0, 0, 0), mti=0, zdiv=20, chunk=1),     # P=256 fused V-CFAR, default windows, range stage off
+    dict(P=256, R=96, C=2, B=1, cfar=(5, 7, 6.0, 0, 9, 20, 6.0, 0, 40, 1), mti=30, zdiv=150, chunk=1),  # wide guard band + large n0: edge substitution on most rows
 ])
 def test_chain_variants(lib, case):
     P, R, C, B = case["P"], case["R"], case["C"], case["B"]
