@@ -74,7 +74,9 @@ typedef struct {
  * MTD/fun_lss_pulse_compression.m:23-25,47-51,58-65).                                            */
 typedef enum {
     RB200_SEG_MF = 0,   /* fun_pulse_compression(taps, x) then (L : L+out_len-1)                     */
-    RB200_SEG_FIR = 1   /* filter(taps,1,x) * scale                                                  */
+    RB200_SEG_FIR = 1,  /* filter(taps,1,x) * scale                                                  */
+    RB200_SEG_MF_CIRC = 2 /* circular matched filter ifft(fft(x,N).*conj(fft(taps,N))), N = out_len in {256,512,4096},
+                           * in_len <= N zero-padded (CW/DMX_SignalProcessing_main_xzr.m:202,348-353)      */
 } rb200_seg_kind;
 
 typedef enum {
@@ -246,6 +248,22 @@ int rb200_motion_para_measure_d(rb200_ctx* ctx, const double* mtd_sum, const dou
                                 const double* k_values, int k_rows, int k_cols, double beam_pos_num, double beam_angle_step,
                                 int fre_ind, double ele_angle_comp, double ele_angle_sys_err, int mtd_0_num,
                                 double* out_r, double* out_v, double* out_ele, int capacity, int* n_out);
+
+/* f4 (DMX script variant): one frame of CW/DMX_SignalProcessing_main_xzr.m:332-426,462-465 for the two monopulse beams.
+ *   short pulse (columns [0,n_short)):  filter(fir_taps,1,x) along range per PRT                       (:344-345)
+ *   long pulse  (the remaining columns, <= fft_num): ifft(fft(x,fft_num) .* conj(fft(mf,fft_num)))     (:202,348-353)
+ *       mf = the (already windowed and normalised) reference, e.g. refData.*kaiser(67,4.5)/norm        (:158-202)
+ *   MTD: fft(x .* mtd_window, mtd_fft_num) along slow time, zero-padded, NOT fftshifted                (:414-418)
+ *   sum = |L| + |R|, diff = |R| - |L|                                                                 (:421-426)
+ *   rows [0, n_blank] and [mtd_fft_num - n_blank, mtd_fft_num) of both sums <- 0 (MTD_0_num = n_blank) (:462-465)
+ * left/right: P x n_range column-major split-complex double (imag may be NULL).  Outputs: mtd_fft_num x n_short and
+ * mtd_fft_num x fft_num column-major real double (any may be NULL; the *_short ones must be NULL when n_short = 0).
+ * The sums feed rb200_execute_cfar_d (n0 = n_blank) and rb200_motion_para_measure_d exactly as in the script.      */
+int rb200_dmx_process_z(rb200_ctx* ctx, const double* left_re, const double* left_im, const double* right_re, const double* right_im,
+                        int P, int n_range, int n_short, const double* fir_taps, int n_fir,
+                        const double* mf_re, const double* mf_im, int n_mf, int fft_num,
+                        const double* mtd_window, int mtd_fft_num, int n_blank,
+                        double* sum_short, double* diff_short, double* sum_long, double* diff_long);
 
 /* f4: sliding-window CPI assembly with the pulse compression done once (MP/main_produce_dataset_win_xzr.m:24-38:
  * echo_win = [frame N; frame N+1], window i = rows round(i*P/n)+1 ... +P, fun_MTD_produce per window).

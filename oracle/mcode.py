@@ -497,6 +497,56 @@ def fun_CFARflag(MTD_data, refCells_R, saveCells_R, T_CFAR_R, CFARmethod_R, refC
 
 
 # ----------------------------------------------------------------------------------------------
+# f4  DMX script variant  (CW/DMX_SignalProcessing_main_xzr.m) -- one frame, two monopulse beams
+# ----------------------------------------------------------------------------------------------
+def hamming(n):
+    """Signal Processing Toolbox ``hamming(n)`` (symmetric): 0.54 - 0.46*cos(2*pi*k/(n-1)); hamming(1) = 1."""
+    n = int(n)
+    if n == 1:
+        return np.ones(1)
+    return 0.54 - 0.46 * np.cos(2.0 * np.pi * np.arange(n) / (n - 1))
+
+
+def dmx_match_filter(ref, beta=4.5, power_norm=True):
+    """matchWaveform2 .* mfWh.' of CW/DMX_SignalProcessing_main_xzr.m:158-166,187-202 (winType 3 = kaiser(len,4.5))."""
+    w = np.asarray(ref, dtype=np.complex128).ravel()                     # :160 refData.'
+    if power_norm:
+        w = w / np.sqrt(np.sum(np.abs(w) ** 2))                          # :166 norm()
+    return w * kaiser(w.size, beta)                                      # :189,202
+
+
+def dmx_frame(left, right, point_short, filter_coef, match_windowed, FFT_num, mtdWh, mtd_FFT_num, MTD_0_num):
+    """CW/DMX_SignalProcessing_main_xzr.m:332-353 (split + pulse compression), :414-426 (MTD, sum / difference),
+    :462-465 (zero-Doppler blanking of the sums).  Returns (sum_short, diff_short, sum_long, diff_long)."""
+    left = np.asarray(left, dtype=np.complex128)
+    right = np.asarray(right, dtype=np.complex128)
+    prtNum = left.shape[0]
+    matchF2 = np.conj(np.fft.fft(match_windowed, FFT_num))               # :202
+    mtdWh = np.asarray(mtdWh, dtype=np.float64).reshape(prtNum, 1)
+    mags = []
+    for beam in (left, right):
+        short = beam[:, :point_short]                                    # :332,335
+        long_ = beam[:, point_short:]                                    # :333,336
+        mf_short = np.zeros(short.shape, dtype=np.complex128)
+        for i in range(prtNum):                                          # :344-345 filter along range, per PRT
+            mf_short[i, :] = matlab_filter_fir(filter_coef, short[i, :]) if point_short else short[i, :]
+        spec = np.fft.fft(long_, FFT_num, axis=1)                        # :348-349 (zero-padded to FFT_num)
+        mf_long = np.fft.ifft(spec * matchF2[None, :], axis=1)           # :352-353
+        mtd_short = np.fft.fft(mf_short * mtdWh, mtd_FFT_num, axis=0)    # :414-415
+        mtd_long = np.fft.fft(mf_long * mtdWh, mtd_FFT_num, axis=0)      # :417-418
+        mags.append((np.abs(mtd_short), np.abs(mtd_long)))
+    sum_short = mags[0][0] + mags[1][0]                                  # :421
+    sum_long = mags[0][1] + mags[1][1]                                   # :422
+    diff_short = mags[1][0] - mags[0][0]                                 # :425
+    diff_long = mags[1][1] - mags[0][1]                                  # :426
+    if MTD_0_num is not None and MTD_0_num >= 0:
+        rows = list(range(0, MTD_0_num + 1)) + list(range(mtd_FFT_num - MTD_0_num, mtd_FFT_num))   # :463 (1-based there)
+        sum_short[rows, :] = 0                                           # :464
+        sum_long[rows, :] = 0                                            # :465
+    return sum_short, diff_short, sum_long, diff_long
+
+
+# ----------------------------------------------------------------------------------------------
 # f3  motionParaMeasure  (CW/motionParaMeasure.m:1-88) -- post-CFAR range / velocity / elevation measurement
 # ----------------------------------------------------------------------------------------------
 def matlab_spline_eval(y, xq):

@@ -148,6 +148,37 @@ class Context:
             out[i] = buf[i * win_len * R:(i + 1) * win_len * R].reshape((int(win_len), R), order="F")
         return out
 
+    def dmx_process(self, left, right, n_short, fir_taps, mf_taps, fft_num, mtd_window, mtd_fft_num, n_blank):
+        """One frame of the DMX script variant (CW/DMX_SignalProcessing_main_xzr.m:332-426,462-465).
+
+        left/right: P x n_range complex beams; returns (sum_short, diff_short, sum_long, diff_long) as
+        mtd_fft_num x n_short / mtd_fft_num x fft_num real matrices (the *_short ones are None when n_short = 0).
+        """
+        left = np.atleast_2d(left)
+        right = np.atleast_2d(right)
+        if left.shape != right.shape:
+            raise B.MatlabDimensionError(B.ERR_DIM_MISMATCH, "dmx_process: the two beams differ in size")
+        P, R = left.shape
+        lre, lim = _split(left)
+        rre, rim = _split(right)
+        fir = np.ascontiguousarray(fir_taps, dtype=np.float64).ravel()
+        mf = np.ascontiguousarray(mf_taps).ravel()
+        mre = np.ascontiguousarray(mf.real, dtype=np.float64)
+        mim = np.ascontiguousarray(mf.imag, dtype=np.float64) if np.iscomplexobj(mf) else None
+        w = np.ascontiguousarray(mtd_window, dtype=np.float64).ravel()
+        if w.size != P:
+            raise B.MatlabDimensionError(B.ERR_DIM_MISMATCH, "dmx_process: mtd_window must have one entry per PRT")
+        n_short, fft_num, mtd_fft_num = int(n_short), int(fft_num), int(mtd_fft_num)
+        ss = np.zeros(mtd_fft_num * n_short) if n_short else None
+        ds = np.zeros(mtd_fft_num * n_short) if n_short else None
+        sl = np.zeros(mtd_fft_num * fft_num)
+        dl = np.zeros(mtd_fft_num * fft_num)
+        self._ck(self._lib.rb200_dmx_process_z(self._h, _fptr(lre), _fptr(lim), _fptr(rre), _fptr(rim), P, R, n_short, _fptr(fir), fir.size,
+                                               _fptr(mre), _fptr(mim), mre.size, fft_num, _fptr(w), mtd_fft_num, int(n_blank),
+                                               _fptr(ss), _fptr(ds), _fptr(sl), _fptr(dl)))
+        shp = lambda a, n: None if a is None else a.reshape((mtd_fft_num, n), order="F")
+        return shp(ss, n_short), shp(ds, n_short), shp(sl, fft_num), shp(dl, fft_num)
+
     def motion_para_measure(self, mtd_sum, mtd_diff, flags, extraDots, rScale, deltaR, rInterpTimes, vScale, deltaV, vInterpTimes,
                             kValues, beamPosNum, beamAngleStep, freInd, eleAngleComp, eleAngleSysErr, MTD_0_num):
         s = np.asfortranarray(np.atleast_2d(mtd_sum), dtype=np.float64)

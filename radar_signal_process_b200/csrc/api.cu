@@ -145,6 +145,8 @@ struct rb200_ctx {
     rb200_config cfg;
     std::string err;
     Plan plan;
+    Plan dmx_plan;                 // private plan of rb200_dmx_process_z (never touches the caller's waveform)
+    unsigned long long dmx_key = 0;
     std::map<std::pair<int, long long>, MtdPlan*> mtd_plans;
     DevBuf gain;
     int gain_n = 0;
@@ -282,17 +284,25 @@ static int build_plan(rb200_ctx* ctx, Plan& plan, const rb200_segment* segs, int
             } else if (s.align != RB200_ALIGN_DELAYED) {
                 return fail(ctx, RB200_ERR_ARG, "set_waveform: FIR segments use DELAYED or GRPDELAY");
             }
+        } else if (s.kind == RB200_SEG_MF_CIRC) {
+            // one FFT tile of exactly out_len points keeps every lag, wrapped ones included: circular correlation
+            if (s.align != RB200_ALIGN_LEADING_EDGE) return fail(ctx, RB200_ERR_ARG, "set_waveform: MF_CIRC segments use LEADING_EDGE");
+            if ((s.out_len != 256 && s.out_len != 512 && s.out_len != 4096) || s.in_len > s.out_len || L > s.out_len)
+                return fail(ctx, RB200_ERR_UNSUPPORTED, "set_waveform: MF_CIRC needs out_len in {256,512,4096} and in_len, n_taps <= out_len");
+            corr_taps[i] = raw;
+            sp.d.pre = 0;
+            sp.d.rot = 0;
         } else {
             return fail(ctx, RB200_ERR_ARG, "set_waveform: unknown segment kind");
         }
-        sp.nt = choose_nt(L);
+        sp.nt = s.kind == RB200_SEG_MF_CIRC ? s.out_len : choose_nt(L);
         sp.d.t_off = (int)taps_all.size();
         for (int k = 0; k < L; ++k) {
             const cd t = corr_taps[i][k] * s.scale;    // direct kernel multiplies by conj(t) -> fold real scale
             taps_all.push_back(make_float2((float)t.real(), (float)t.imag()));
         }
         if (sp.nt) {
-            sp.d.V = sp.nt - L + 1;
+            sp.d.V = s.kind == RB200_SEG_MF_CIRC ? sp.nt : sp.nt - L + 1;
             sp.d.h_off = (int)h_total;
             h_total += sp.nt;
         }
@@ -428,6 +438,41 @@ static int get_mtd_plan(rb200_ctx* ctx, int P, double beta, MtdPlan** out) {
     std::vector<double> w = kaiser_window(P, beta);
     std::vector<float> wf(P);
     for (int i = 0; i < P; ++i) wf[i] = (float)w[i];
+    mp->h_window = wf;
+    std::vector<float2> tw(P);
+    for (int m = 0; m < P; ++m) {
+        const double a = -2.0 * M_PI * m / P;
+        tw[m] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    factor_radices(P, mp->radix, &mp->n_stages);
+    cudaError_t e = mp->window.ensure(P * sizeof(float));
+    if (e == cudaSuccess) e = mp->tw.ensure(P * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mp->window.p, wf.data(), P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mp->tw.p, tw.data(), P * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        delete mp;
+        ctx->err = std::string("mtd plan: ") + cudaGetErrorString(e);
+        return RB200_ERR_CUDA;
+    }
+    ctx->mtd_plans[key] = mp;
+    *out = mp;
+    return RB200_OK;
+}
+
+// MTD plan with a caller-supplied slow-time window of nw <= P entries (zero padding beyond), keyed by its contents
+static int get_mtd_plan_custom(rb200_ctx* ctx, int P, const double* w, int nw, MtdPlan** out) {
+    unsigned long long hsh = 1469598103934665603ull;
+    const unsigned char* bytes = reinterpret_cast<const unsigned char*>(w);
+    for (size_t i = 0; i < (size_t)nw * sizeof(double); ++i) hsh = (hsh ^ bytes[i]) * 1099511628211ull;
+    hsh ^= (unsigned long long)nw * 0x9e3779b97f4a7c15ull;
+    auto key = std::make_pair(-P, (long long)hsh);          // negative P: never collides with the Kaiser plans
+    auto it = ctx->mtd_plans.find(key);
+    if (it != ctx->mtd_plans.end()) { *out = it->second; return RB200_OK; }
+    MtdPlan* mp = new MtdPlan();
+    mp->P = P;
+    std::vector<float> wf(P, 0.f);
+    for (int i = 0; i < nw; ++i) wf[i] = (float)w[i];
     mp->h_window = wf;
     std::vector<float2> tw(P);
     for (int m = 0; m < P; ++m) {
@@ -591,6 +636,7 @@ extern "C" int rb200_destroy(rb200_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->plan.release();
+    c->dmx_plan.release();
     for (auto& kv : c->mtd_plans) {
         kv.second->window.release();
         kv.second->tw.release();
@@ -871,6 +917,125 @@ extern "C" int rb200_mtd_produce_windows_z(rb200_ctx* c, const double* echo_re, 
         c->launches++;
         CK(c, cudaMemcpyAsync(out + (size_t)i * nw, c->s_out_re.p, nw * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RB200_OK;
+}
+
+extern "C" int rb200_dmx_process_z(rb200_ctx* c, const double* left_re, const double* left_im, const double* right_re,
+                                   const double* right_im, int P, int n_range, int n_short, const double* fir_taps, int n_fir,
+                                   const double* mf_re, const double* mf_im, int n_mf, int fft_num, const double* mtd_window,
+                                   int mtd_fft_num, int n_blank, double* sum_short, double* diff_short, double* sum_long,
+                                   double* diff_long) {
+    if (!c || !left_re || !right_re || !mf_re || !mtd_window || P < 1 || n_range < 1 || n_short < 0 || n_short >= n_range || n_mf < 1 ||
+        (n_short > 0 && (!fir_taps || n_fir < 1)) || (n_short == 0 && (sum_short || diff_short)))
+        return fail(c, RB200_ERR_ARG, "dmx_process: bad argument");
+    const int n_long = n_range - n_short;
+    if ((fft_num != 256 && fft_num != 512 && fft_num != 4096) || n_long > fft_num || n_mf > fft_num)
+        return fail(c, RB200_ERR_UNSUPPORTED, "dmx_process: FFT_num must be 256, 512 or 4096 and hold the long-pulse samples and the reference");
+    if (mtd_fft_num < P || mtd_fft_num > mtd_generic_max_p())
+        return fail(c, RB200_ERR_UNSUPPORTED, "dmx_process: mtd_FFT_num must be in [prtNum, 12288]");
+    if (n_blank >= 0 && 2 * n_blank + 1 > mtd_fft_num) return fail(c, RB200_ERR_INDEX, "dmx_process: zeroSetFlagMTD exceeds the Doppler axis");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    // ---- waveform plan (rebuilt only when the taps or the geometry change) ----
+    unsigned long long key = 1469598103934665603ull;
+    auto mix = [&key](const void* p, size_t nbytes) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < nbytes; ++i) key = (key ^ b[i]) * 1099511628211ull;
+    };
+    const int geo[5] = {n_range, n_short, n_fir, n_mf, fft_num};
+    mix(geo, sizeof geo);
+    if (n_short > 0) mix(fir_taps, (size_t)n_fir * sizeof(double));
+    mix(mf_re, (size_t)n_mf * sizeof(double));
+    if (mf_im) mix(mf_im, (size_t)n_mf * sizeof(double));
+    if (!c->dmx_plan.valid || c->dmx_key != key) {
+        rb200_segment segs[2];
+        memset(segs, 0, sizeof segs);
+        int ns = 0;
+        if (n_short > 0) {
+            segs[ns].kind = RB200_SEG_FIR;
+            segs[ns].align = RB200_ALIGN_DELAYED;
+            segs[ns].in_start = 0;
+            segs[ns].in_len = n_short;
+            segs[ns].out_start = 0;
+            segs[ns].out_len = n_short;
+            segs[ns].taps_re = fir_taps;
+            segs[ns].n_taps = n_fir;
+            segs[ns].scale = 1.0;
+            ++ns;
+        }
+        segs[ns].kind = RB200_SEG_MF_CIRC;
+        segs[ns].align = RB200_ALIGN_LEADING_EDGE;
+        segs[ns].in_start = n_short;
+        segs[ns].in_len = n_long;
+        segs[ns].out_start = n_short;
+        segs[ns].out_len = fft_num;
+        segs[ns].taps_re = mf_re;
+        segs[ns].taps_im = mf_im;
+        segs[ns].n_taps = n_mf;
+        segs[ns].scale = 1.0;
+        ++ns;
+        int rc = build_plan(c, c->dmx_plan, segs, ns);
+        if (rc) return rc;
+        c->dmx_key = key;
+    }
+    // ---- both beams as planar lines [beam][prt][range] ----
+    const int R_out = n_short + fft_num;
+    const size_t n_in = (size_t)P * n_range, n_pc = (size_t)P * R_out, n_rdm = (size_t)mtd_fft_num * R_out;
+    CK(c, c->s_a.ensure(2 * n_in * sizeof(float2)));
+    CK(c, c->s_b.ensure(2 * n_pc * sizeof(float2)));
+    CK(c, c->s_c.ensure(2 * n_rdm * sizeof(float)));
+    const double* beams[2][2] = {{left_re, left_im}, {right_re, right_im}};
+    for (int b = 0; b < 2; ++b) {
+        const double *dre, *dim;
+        int rc = upload_z(c, beams[b][0], beams[b][1], n_in, &dre, &dim);
+        if (rc) return rc;
+        CK(c, launch_z_to_planar(dre, dim, c->s_a.as<float2>() + b * n_in, P, n_range, c->stream));
+        c->launches++;
+        CK(c, cudaStreamSynchronize(c->stream));     // the staging buffers are re-used by the second beam
+    }
+    int rc = run_pc(c, c->dmx_plan, false, c->s_a.p, c->s_b.as<float2>(), n_range, R_out, 1, 1, 0, 2 * P, nullptr, c->stream);
+    if (rc) return rc;
+    // ---- slow-time FFT, zero-padded to mtd_fft_num, natural order ----
+    MtdPlan* mp = nullptr;
+    rc = get_mtd_plan_custom(c, mtd_fft_num, mtd_window, P, &mp);
+    if (rc) return rc;
+    MtdParams p;
+    memset(&p, 0, sizeof p);
+    p.in = c->s_b.as<float2>();
+    p.out = c->s_c.as<float>();
+    p.window = mp->window.as<float>();
+    p.tw = mp->tw.as<float2>();
+    p.P = mtd_fft_num;
+    p.in_rows = P;
+    p.no_shift = 1;
+    p.in_ld = R_out;
+    p.out_ld = R_out;
+    p.cols = R_out;
+    p.zv_lo = 1;
+    p.zv_hi = 0;
+    p.n_stages = mp->n_stages;
+    for (int i = 0; i < mp->n_stages; ++i) p.radix[i] = mp->radix[i];
+    CK(c, launch_mtd(p, 2, c->stream));
+    c->launches++;
+    // ---- sum / difference channels, blanking, MATLAB layout ----
+    const float* ml = c->s_c.as<float>();
+    const float* mr = ml + n_rdm;
+    const size_t n_s = (size_t)mtd_fft_num * n_short, n_l = (size_t)mtd_fft_num * fft_num;
+    CK(c, c->s_out_re.ensure(std::max<size_t>(n_s + n_l, 1) * sizeof(double)));
+    CK(c, c->s_out_im.ensure(std::max<size_t>(n_s + n_l, 1) * sizeof(double)));
+    double* d_sum = c->s_out_re.as<double>();
+    double* d_diff = c->s_out_im.as<double>();
+    if (n_short > 0) {
+        CK(c, launch_dmx_combine(ml, mr, R_out, 0, d_sum, d_diff, mtd_fft_num, n_short, n_blank, c->stream));
+        c->launches++;
+    }
+    CK(c, launch_dmx_combine(ml, mr, R_out, n_short, d_sum + n_s, d_diff + n_s, mtd_fft_num, fft_num, n_blank, c->stream));
+    c->launches++;
+    if (sum_short) CK(c, cudaMemcpyAsync(sum_short, d_sum, n_s * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (diff_short) CK(c, cudaMemcpyAsync(diff_short, d_diff, n_s * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (sum_long) CK(c, cudaMemcpyAsync(sum_long, d_sum + n_s, n_l * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (diff_long) CK(c, cudaMemcpyAsync(diff_long, d_diff + n_s, n_l * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return RB200_OK;
 }

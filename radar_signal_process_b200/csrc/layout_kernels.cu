@@ -60,6 +60,32 @@ __global__ void f32_rowmajor_to_d_colmajor_kernel(const float* __restrict__ in, 
     }
 }
 
+// DMX sum / difference channel (CW/DMX_SignalProcessing_main_xzr.m:421-426,462-465): magnitudes of the two beams,
+// row-major float [beam][rows][ld] (columns c0 .. c0+cols-1 used) -> column-major double sum = |L|+|R| with rows
+// [0, n_blank] and [rows-n_blank, rows) zeroed, diff = |R|-|L| (not blanked).
+__global__ void dmx_combine_kernel(const float* __restrict__ left, const float* __restrict__ right, int ld, int c0, double* __restrict__ sum,
+                                   double* __restrict__ diff, int rows, int cols, int n_blank) {
+    __shared__ float tl[32][33], tr[32][33];
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    for (int di = threadIdx.y; di < 32; di += blockDim.y) {
+        const int i = i0 + di, j = j0 + threadIdx.x;
+        if (i < rows && j < cols) {
+            tl[di][threadIdx.x] = left[(size_t)i * ld + c0 + j];
+            tr[di][threadIdx.x] = right[(size_t)i * ld + c0 + j];
+        }
+    }
+    __syncthreads();
+    for (int dj = threadIdx.y; dj < 32; dj += blockDim.y) {
+        const int i = i0 + threadIdx.x, j = j0 + dj;
+        if (i < rows && j < cols) {
+            const double a = (double)tl[threadIdx.x][dj], b = (double)tr[threadIdx.x][dj];
+            const bool blank = n_blank >= 0 && (i <= n_blank || i >= rows - n_blank);
+            if (sum) sum[(size_t)i + (size_t)rows * j] = blank ? 0.0 : a + b;
+            if (diff) diff[(size_t)i + (size_t)rows * j] = b - a;
+        }
+    }
+}
+
 __global__ void u8_to_d_kernel(const uint8_t* __restrict__ in, double* __restrict__ out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] ? 1.0 : 0.0;
@@ -88,6 +114,12 @@ cudaError_t launch_planar_to_z(const float2* in, double* re, double* im, int row
 cudaError_t launch_f32_rowmajor_to_d_colmajor(const float* in, double* out, int rows, int cols, cudaStream_t st) {
     if (rows <= 0 || cols <= 0) return cudaSuccess;
     f32_rowmajor_to_d_colmajor_kernel<<<tgrid(rows, cols), dim3(32, 8), 0, st>>>(in, out, rows, cols);
+    return cudaGetLastError();
+}
+cudaError_t launch_dmx_combine(const float* left, const float* right, int ld, int c0, double* sum, double* diff, int rows, int cols,
+                               int n_blank, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0 || (!sum && !diff)) return cudaSuccess;
+    dmx_combine_kernel<<<tgrid(rows, cols), dim3(32, 8), 0, st>>>(left, right, ld, c0, sum, diff, rows, cols, n_blank);
     return cudaGetLastError();
 }
 cudaError_t launch_u8_to_d(const uint8_t* in, double* out, size_t n, cudaStream_t st) {

@@ -206,11 +206,12 @@ __global__ void mtd_generic_kernel(const MtdParams p) {
     const int slab = blockIdx.y;
     const int r = blockIdx.x * TR + rl;
     const bool ok = r < p.cols;
-    const float2* col = p.in + (size_t)slab * P * p.in_ld + r;
+    const int rows_in = p.in_rows > 0 ? p.in_rows : P;
+    const float2* col = p.in + (size_t)slab * rows_in * p.in_ld + r;
     for (int prt = threadIdx.y; prt < P; prt += blockDim.y) {
         float2 x = make_float2(0.f, 0.f);
-        if (ok) x = mtd_load(col, prt, P, p.in_ld, p.mti_lag);
-        a[prt * TR + rl] = cscale(x, __ldg(p.window + prt));
+        if (ok && prt < rows_in) x = cscale(mtd_load(col, prt, rows_in, p.in_ld, p.mti_lag), __ldg(p.window + prt));
+        a[prt * TR + rl] = x;
     }
     __syncthreads();
     int Ns = 1;
@@ -240,7 +241,7 @@ __global__ void mtd_generic_kernel(const MtdParams p) {
     }
     if (ok) {
         float* out = p.out + (size_t)slab * P * p.out_ld + r;
-        const int half = P / 2;
+        const int half = p.no_shift ? 0 : P / 2;
         for (int m = threadIdx.y; m < P; m += blockDim.y) {
             int row = m + half;
             if (row >= P) row -= P;
@@ -283,8 +284,9 @@ static cudaError_t launch_fast(const MtdParams& p, int n_slabs, cudaStream_t st)
 
 cudaError_t launch_mtd(const MtdParams& p, int n_slabs, cudaStream_t st) {
     if (p.cols <= 0 || n_slabs <= 0) return cudaSuccess;
-    if (p.P == 64) return launch_fast<8, 64>(p, n_slabs, st);
-    if (p.P == 256) return launch_fast<16, 32>(p, n_slabs, st);
+    const bool plain = p.in_rows == 0 && !p.no_shift;
+    if (p.P == 64 && plain) return launch_fast<8, 64>(p, n_slabs, st);
+    if (p.P == 256 && plain) return launch_fast<16, 32>(p, n_slabs, st);
     // generic
     int TR = 32;
     while (TR > 1 && (size_t)2 * p.P * TR * sizeof(float2) > 96 * 1024) TR >>= 1;

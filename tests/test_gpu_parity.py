@@ -374,7 +374,7 @@ def test_chain_detection_overflow_is_reported(lib):
     dict(P=48, R=300, C=2, B=2, cfar=(5, 7, 5.0, 0, 4, 3, 5.0, 0, 0, 1), mti=0, zdiv=0, chunk=2),       # P = 2^4*3, no zero-velocity mask
     dict(P=256, R=333, C=2, B=2, cfar=(4, 2, 5.0, 1, 6, 3, 5.0, 1, 3, 1), mti=0, zdiv=150, chunk=1),    # P=256 fused V-CFAR, run-time windows, SO, ragged R
     dict(P=256, R=288, C=1, B=1, cfar=(5, 7, 6.0, 0, 5, 7, 6.0, 0, 0, 0), mti=0, zdiv=20, chunk=1),     # P=256 fused V-CFAR, default windows, range stage off
-    dict(P=256, R=96, C=2, B=1, cfar=(5, 7, 6.0, 0, 9, 20, 6.0, 0, 40, 1), mti=30, zdiv=150, chunk=1),  # wide guard band + large n0: edge substitution on most rows
+    dict(P=256, R=224, C=2, B=1, cfar=(5, 7, 6.0, 0, 9, 20, 6.0, 0, 40, 1), mti=30, zdiv=150, chunk=1),  # wide guard band + large n0: edge substitution on most rows
 ])
 def test_chain_variants(lib, case):
     P, R, C, B = case["P"], case["R"], case["C"], case["B"]
@@ -598,3 +598,73 @@ def test_capture_files_to_detections_end_to_end(lib, tmp_path):
         rdm, dets, n = ctx.chain(batch, B)
     _close(rdm, out["rdm"])
     _compare_flags(dets, out, B, C, P, R, lib)
+
+
+def _dmx_inputs(P, n_range, n_short, seed):
+    rng = np.random.default_rng(seed)
+    ref = mcode.load_ref("refDDCDataMF1")
+    mf = mcode.dmx_match_filter(ref)
+    beams = []
+    for b in range(2):
+        x = np.round(rng.normal(0, 40, (P, n_range))) + 1j * np.round(rng.normal(0, 40, (P, n_range)))
+        # a long-pulse echo near the end of the PRT (wraps around in the circular compression) and one in the middle
+        for r0, dop, amp in ((n_range - 30, 0.11, 300.0), (n_short + 100, -0.23, 200.0 * (1 + b))):
+            n = min(ref.size, n_range - r0)
+            x[:, r0:r0 + n] += amp * ref[None, :n] * np.exp(2j * np.pi * dop * np.arange(P))[:, None]
+        if n_short:
+            x[:, 20] += 500.0 * np.exp(2j * np.pi * 0.05 * np.arange(P))      # short-pulse return
+        beams.append(x)
+    return beams[0], beams[1], mf
+
+
+@pytest.mark.parametrize("P,n_range,n_short,fft_num,mtd_fft,n0", [
+    (96, 566, 62, 512, 128, 3),        # reduced slow-time length, script geometry in range (62 + 504 -> 512)
+    (1536, 566, 62, 512, 2048, 27),    # the script's own sizes (prtNum 1536, FFT_num 512, mtd_FFT_num 2048)
+    (40, 200, 0, 256, 40, 0),          # no short pulse, no Doppler zero padding
+])
+def test_dmx_frame_matches_oracle(lib, P, n_range, n_short, fft_num, mtd_fft, n0):
+    """f4: DMX script variant -- FIR short pulse, circular matched filter, Hamming zero-padded MTD, sum / difference."""
+    left, right, mf = _dmx_inputs(P, n_range, n_short, seed=P + n_range)
+    win = mcode.hamming(P)
+    want = mcode.dmx_frame(left, right, n_short, mcode.FILTER_COEF_INT, mf, fft_num, win, mtd_fft, n0)
+    with lib.Context(0, n_prt=8, n_range=64, n_lanes=1) as ctx:
+        got = ctx.dmx_process(left, right, n_short, mcode.FILTER_COEF_INT, mf, fft_num, win, mtd_fft, n0)
+        again = ctx.dmx_process(left, right, n_short, mcode.FILTER_COEF_INT, mf, fft_num, win, mtd_fft, n0)   # cached plan
+    for g, a, w in zip(got, again, want):
+        if n_short == 0 and w.shape[1] == 0:
+            assert g is None
+            continue
+        assert g.shape == w.shape
+        np.testing.assert_array_equal(g, a)
+        scale = np.abs(w).max()
+        assert np.abs(g - w).max() <= RTOL * scale, (np.abs(g - w).max(), scale)
+    # blanked rows are exactly zero in the sums and untouched in the differences
+    assert np.all(got[2][:n0 + 1] == 0) and np.all(got[2][mtd_fft - n0:] == 0)
+    assert np.any(got[3][:n0 + 1] != 0)
+
+
+def test_dmx_sums_feed_execute_cfar_like_the_script(lib):
+    """DMX script :468-472: executeCFAR on the blanked long-pulse sum with n0 = MTD_0_num."""
+    P, n_range, n_short, fft_num, mtd_fft, n0 = 96, 566, 62, 512, 128, 3
+    left, right, mf = _dmx_inputs(P, n_range, n_short, seed=77)
+    win = mcode.hamming(P)
+    want = mcode.dmx_frame(left, right, n_short, mcode.FILTER_COEF_INT, mf, fft_num, win, mtd_fft, n0)
+    with lib.Context(0, n_prt=8, n_range=64, n_lanes=1) as ctx:
+        got = ctx.dmx_process(left, right, n_short, mcode.FILTER_COEF_INT, mf, fft_num, win, mtd_fft, n0)
+    f, fv = lib.executeCFAR(got[2], 5, 7, 7.0, 0, 5, 7, 7.0, 0, n0, 1)
+    wf, wfv = mcode.executeCFAR(got[2], 5, 7, 7.0, 0, 5, 7, 7.0, 0, n0, 1)
+    np.testing.assert_array_equal(f, wf)
+    np.testing.assert_array_equal(fv, wfv)
+    assert fv.sum() > 0
+
+
+def test_dmx_argument_errors(lib):
+    left, right, mf = _dmx_inputs(16, 120, 10, seed=1)
+    win = mcode.hamming(16)
+    with lib.Context(0, n_prt=8, n_range=64, n_lanes=1) as ctx:
+        with pytest.raises(lib.RadarB200Error):       # FFT_num not a supported size
+            ctx.dmx_process(left, right, 10, mcode.FILTER_COEF_INT, mf, 300, win, 16, 0)
+        with pytest.raises(lib.RadarB200Error):       # long pulse longer than FFT_num (fft(x, n) would truncate)
+            ctx.dmx_process(left, right, 10, mcode.FILTER_COEF_INT, mf[:20], 256, np.ones(16), 8, 0)
+        with pytest.raises(lib.RadarB200Error):       # blanking wider than the Doppler axis
+            ctx.dmx_process(left, right, 10, mcode.FILTER_COEF_INT, mf, 256, win, 16, 9)

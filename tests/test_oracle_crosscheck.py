@@ -140,3 +140,46 @@ def test_unpack_ddc_known_answer():
     out = mcode.unpack_ddc_i16(raw, 2, 2)
     want = np.array([[1 - 2j, 3 - 4j], [5 - 6j, 7 - 8j]])
     np.testing.assert_array_equal(out, want)
+
+
+def test_hamming_matches_scipy():
+    import scipy.signal.windows as ssw
+    for n in (2, 67, 96, 1536):
+        np.testing.assert_allclose(mcode.hamming(n), ssw.hamming(n, sym=True), rtol=1e-13, atol=1e-15)
+
+
+def test_dmx_long_pulse_is_circular_correlation_mod_fft_num():
+    # CW/DMX_SignalProcessing_main_xzr.m:202,348-353: ifft(fft(x,512).*conj(fft(h,512))) = sum_k x[(n+k) mod 512] conj(h[k])
+    rng = np.random.default_rng(4)
+    P, n_long, N = 3, 504, 512
+    h = mcode.dmx_match_filter(mcode.load_ref("refDDCDataMF1"))
+    x = rng.standard_normal((P, n_long)) + 1j * rng.standard_normal((P, n_long))
+    z = np.zeros((P, 0))
+    _, _, s_long, d_long = mcode.dmx_frame(x, 2 * x, 0, mcode.FILTER_COEF_INT, h, N, np.ones(P), P, None)
+    xp = np.concatenate([x, np.zeros((P, N - n_long))], axis=1)
+    want = np.zeros((P, N), dtype=complex)
+    for n in range(N):
+        for k in range(h.size):
+            want[:, n] += xp[:, (n + k) % N] * np.conj(h[k])
+    mag = np.abs(np.fft.fft(want, axis=0))
+    np.testing.assert_allclose(s_long, 3 * mag, rtol=1e-9, atol=1e-9)       # |L| + |R| with R = 2 L
+    np.testing.assert_allclose(d_long, mag, rtol=1e-9, atol=1e-9)          # |R| - |L|
+    assert np.isclose(np.sum(np.abs(h / mcode.kaiser(h.size, 4.5)) ** 2), 1.0)   # energy-normalised before the taper
+
+
+def test_dmx_blanking_rows_and_short_pulse_fir():
+    rng = np.random.default_rng(9)
+    P, n_short, n_long, N, M, n0 = 8, 20, 30, 256, 16, 2
+    x = rng.standard_normal((P, n_short + n_long)) + 1j * rng.standard_normal((P, n_short + n_long))
+    h = np.ones(4)
+    ss, ds, sl, dl = mcode.dmx_frame(x, x, n_short, mcode.FILTER_COEF_INT, h, N, mcode.hamming(P), M, n0)
+    assert ss.shape == (M, n_short) and sl.shape == (M, N)
+    assert np.all(ss[[0, 1, 2, 14, 15]] == 0) and np.all(sl[[0, 1, 2, 14, 15]] == 0) and np.all(ss[3:14] > 0)
+    assert np.all(ds == 0) and np.all(dl == 0)                                # identical beams: zero difference channel
+    want = np.abs(np.fft.fft(ss_ref(x[:, :n_short], P) * mcode.hamming(P)[:, None], M, axis=0)) * 2
+    np.testing.assert_allclose(ss[3:14], want[3:14], rtol=1e-10, atol=1e-10)
+
+
+def ss_ref(short, P):
+    import scipy.signal as sig
+    return sig.lfilter(mcode.FILTER_COEF_INT, [1.0], short, axis=1)           # un-normalised taps, no delay compensation (:344)
