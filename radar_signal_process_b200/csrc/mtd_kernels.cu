@@ -153,27 +153,56 @@ mtd_fast_kernel(const MtdParams p) {
         }
     }
     const float inv_ref = 1.f / (float)ref;
+    // decisions of this thread's R rows as a bit mask; `tested` (warp-uniform) marks the rows inside [v_lo, v_hi)
+    unsigned hits = 0u, tested = 0u;
+    const bool interior = y0 - H >= 0 && y0 + R - 1 + H <= nv - 1;      // both windows fit for all R rows (most threads)
+    if (interior) {
+        tested = (1u << R) - 1u;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const float a = ml[i] * inv_ref, b = mr[i] * inv_ref;
+            const float mu = p.cf.meth_v == 0 ? fmaxf(a, b) : fminf(a, b);
+            hits |= (xc[i] >= mu * p.t_v ? 1u : 0u) << i;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int y = y0 + i;
+            if (y < 0 || y >= nv) continue;
+            const bool okL = y - H >= 0;
+            const bool okR = y + H <= nv - 1;
+            if (!okL && !okR) {                        // MATLAB: index exceeds array bounds
+                if (threadIdx.x == 0) *p.err_flag = 1;
+                continue;
+            }
+            tested |= 1u << i;
+            const float a = (okL ? ml[i] : mr[i]) * inv_ref;
+            const float b = (okR ? mr[i] : ml[i]) * inv_ref;
+            const float mu = p.cf.meth_v == 0 ? fmaxf(a, b) : fminf(a, b);
+            hits |= (xc[i] >= mu * p.t_v ? 1u : 0u) << i;
+        }
+    }
+    if (!ok) hits = 0u;
     const int Rw = (p.cf.R + 31) / 32;
     const int lane = threadIdx.x & 31;
     uint32_t* vm = p.vmask + ((size_t)slab * p.cf.V + u * R) * Rw + (r >> 5);   // a warp covers 32 consecutive columns
     const bool vm_ok = lane == 0 && (r >> 5) < Rw;
+    const bool any = __any_sync(0xffffffffu, hits != 0u);
+    if (!any) {                                        // the common case: no detection in these 32 columns x R rows
+        if (vm_ok) {
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                if ((tested >> i) & 1u) vm[i * Rw] = 0u;
+        }
+        return;
+    }
     const uint32_t det_hdr = (uint32_t)(slab % p.cf.n_lanes) << 16 |
                              (uint32_t)(p.cf.range_stage ? RB200_DET_V : (RB200_DET_V | RB200_DET_2D)) << 24;
     const uint32_t det_cpi = (uint32_t)(p.cf.cpi0 + slab / p.cf.n_lanes);
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-        const int y = y0 + i;
-        if (y < 0 || y >= nv) continue;                // warp-uniform: u is warp-uniform for TR >= 32
-        const bool okL = y - H >= 0;
-        const bool okR = y + H <= nv - 1;
-        if (!okL && !okR) {                            // MATLAB: index exceeds array bounds
-            if (threadIdx.x == 0) *p.err_flag = 1;
-            continue;
-        }
-        const float a = (okL ? ml[i] : mr[i]) * inv_ref;
-        const float b = (okR ? mr[i] : ml[i]) * inv_ref;
-        const float mu = p.cf.meth_v == 0 ? fmaxf(a, b) : fminf(a, b);
-        const bool hit = ok && xc[i] >= mu * p.t_v;
+        if (!((tested >> i) & 1u)) continue;           // warp-uniform: u is warp-uniform for TR >= 32
+        const bool hit = (hits >> i) & 1u;
         const unsigned ball = __ballot_sync(0xffffffffu, hit);
         if (vm_ok) vm[i * Rw] = ball;
         if (ball == 0) continue;

@@ -155,7 +155,7 @@ pc_fft_kernel(const PcParams p) {
 // the CTA is still transforming the previous item, so the global-load latency never stalls the
 // butterflies.  Grid = resident CTAs (SMs x 3); items (line group, tile) are taken round-robin.
 // ---------------------------------------------------------------------------------------------
-template <int R, int S>
+template <int R, int S, bool GAIN>
 __global__ void __launch_bounds__(16 * (ipow(R, S) / R), PcOcc<R, S, 16>::min_blocks)
 pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
     constexpr int LT = 16;
@@ -212,6 +212,16 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
         const PcSegDev& sg = p.segs[tile.x];
         const int in_off = tile.y * sg.V - sg.pre;
 
+        // iSTC gains of this thread's samples (MP/fun_iSTC.m:14) are fetched before waiting for the raw tile, so their
+        // global-load latency hides behind the TMA wait instead of stalling the first butterfly
+        float gv[GAIN ? R : 1];
+        if (GAIN) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int rs = in_off + u + j * NB;
+                gv[GAIN ? j : 0] = (rs >= 0 && rs < sg.in_len) ? __ldg(p.gain + sg.in_start + rs) : 0.f;
+            }
+        }
         mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
         float2 v[R];
         {
@@ -234,12 +244,9 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
                     v[j].y = (float)(w >> 16);
                 }
             }
-            if (p.gain) {
+            if (GAIN) {
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const int rs = in_off + u + j * NB;
-                    if (rs >= 0 && rs < sg.in_len) v[j] = cscale(v[j], __ldg(p.gain + sg.in_start + rs));
-                }
+                for (int j = 0; j < R; ++j) v[j] = cscale(v[j], gv[GAIN ? j : 0]);   // samples outside the segment are 0 already
             }
         }
         // generic-proxy reads of the staging buffer are ordered before the TMA (async-proxy) refill that thread 0
@@ -387,14 +394,21 @@ cudaError_t launch_pc_fft_tma(const PcParams& p, int n_tiles, int n_groups, int 
     constexpr int R = 16, S = 2, NT = 256, LT = 16;
     const size_t fft_bytes = ((size_t)LT * (NT + 1) * sizeof(float2) + 127) / 128 * 128;
     const size_t smem = fft_bytes + 2 * (size_t)NT * LT * 4 + ((size_t)tw_block_off<R, S>(S - 1) + h_entries) * sizeof(float2);
-    static size_t configured[64] = {};
-    cudaError_t ce = ensure_dynamic_smem(pc_fft_tma_kernel<R, S>, smem, configured);
-    if (ce != cudaSuccess) return ce;
     const long long n_items = (long long)n_tiles * n_groups;
     if (n_items <= 0 || n_items > 0x7fffffffLL) return n_items <= 0 ? cudaSuccess : cudaErrorInvalidConfiguration;
     const int per_sm = std::max(1, std::min(ctas_per_sm, (int)PcOcc<R, S, LT>::min_blocks));
     const int grid = (int)std::min<long long>(n_items, (long long)n_sms * per_sm);
-    pc_fft_tma_kernel<R, S><<<grid, LT * (NT / R), smem, st>>>(p, (int)n_items, n_tiles, h_entries);
+    if (p.gain) {
+        static size_t configured[64] = {};
+        cudaError_t ce = ensure_dynamic_smem(pc_fft_tma_kernel<R, S, true>, smem, configured);
+        if (ce != cudaSuccess) return ce;
+        pc_fft_tma_kernel<R, S, true><<<grid, LT * (NT / R), smem, st>>>(p, (int)n_items, n_tiles, h_entries);
+    } else {
+        static size_t configured[64] = {};
+        cudaError_t ce = ensure_dynamic_smem(pc_fft_tma_kernel<R, S, false>, smem, configured);
+        if (ce != cudaSuccess) return ce;
+        pc_fft_tma_kernel<R, S, false><<<grid, LT * (NT / R), smem, st>>>(p, (int)n_items, n_tiles, h_entries);
+    }
     return cudaGetLastError();
 }
 
