@@ -128,7 +128,12 @@ mtd64_tma_kernel(const Mtd64Params p, int tiles_per_slab, int n_items) {
     }
 }
 
-__device__ __forceinline__ bool cfar_decide_f32(const float* __restrict__ row, int y, int N, int ref, int guard, float thr, int method, int* err_flag) {
+// REF > 0: the reference-cell count as a compile-time constant, so that both window loops unroll and their loads are
+// issued back to back (one memory round trip per decision instead of one per reference cell -- the sparse range stage
+// is latency-bound); REF = 0: run-time `ref`.
+template <int REF>
+__device__ __forceinline__ bool cfar_decide_f32(const float* __restrict__ row, int y, int N, int ref_rt, int guard, float thr, int method, int* err_flag) {
+    const int ref = REF > 0 ? REF : ref_rt;
     const int l1 = y - guard - ref;
     const int r1 = y + guard + 1;
     const bool okL = l1 >= 0;
@@ -138,33 +143,67 @@ __device__ __forceinline__ bool cfar_decide_f32(const float* __restrict__ row, i
         return false;
     }
     float sl = 0.f, sr = 0.f;
-    if (okL) for (int j = 0; j < ref; ++j) sl += row[l1 + j];
-    if (okR) for (int j = 0; j < ref; ++j) sr += row[r1 + j];
+    const float x = __ldg(row + y);
+    if (REF > 0) {
+        float wl[REF > 0 ? REF : 1], wr[REF > 0 ? REF : 1];
+#pragma unroll
+        for (int j = 0; j < REF; ++j) {
+            wl[j] = okL ? __ldg(row + l1 + j) : 0.f;
+            wr[j] = okR ? __ldg(row + r1 + j) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < REF; ++j) {
+            sl += wl[j];
+            sr += wr[j];
+        }
+    } else {
+        if (okL) for (int j = 0; j < ref; ++j) sl += __ldg(row + l1 + j);
+        if (okR) for (int j = 0; j < ref; ++j) sr += __ldg(row + r1 + j);
+    }
     const float mr = sr / (float)ref, ml = sl / (float)ref;
     const float a = okL ? ml : mr;
     const float b = okR ? mr : ml;
     const float mu = method == 0 ? fmaxf(a, b) : fminf(a, b);
-    return row[y] >= mu * thr;
+    return x >= mu * thr;
 }
 
+template <int REF>
 __device__ __forceinline__ int cfar_elect_f32(const float* __restrict__ row, int r, const CfarParams& p, float t_r, int* err_flag) {
+    // the three decisions are evaluated unconditionally first (their loads overlap), then combined in column order
+    bool pass[3];
+    float x[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int c = r + d - 1;
+        const bool inside = c >= 0 && c < p.R;
+        pass[d] = inside && cfar_decide_f32<REF>(row, inside ? c : r, p.R, p.ref_r, p.guard_r, t_r, p.meth_r, err_flag);
+        x[d] = inside ? __ldg(row + c) : 0.f;
+    }
     int best = -1;
     float bestv = 0.f;
 #pragma unroll
-    for (int d = -1; d <= 1; ++d) {
-        const int c = r + d;
-        if (c < 0 || c >= p.R) continue;
-        if (!cfar_decide_f32(row, c, p.R, p.ref_r, p.guard_r, t_r, p.meth_r, err_flag)) continue;
-        const float x = row[c];
-        if (best < 0 || x > bestv) { best = c; bestv = x; }
-    }
+    for (int d = 0; d < 3; ++d)
+        if (pass[d] && (best < 0 || x[d] > bestv)) { best = r + d - 1; bestv = x[d]; }
     return best;
+}
+
+// One list slot for every thread of the warp that is currently converged here, with a single atomic per warp
+// (same-address atomics serialise in L2: thousands of hits per chunk would otherwise queue up one by one).
+__device__ __forceinline__ int warp_agg_slot(int* counter) {
+    const unsigned am = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(am) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(am));
+    base = __shfl_sync(am, base, leader);
+    return base + __popc(am & ((1u << lane) - 1u));
 }
 
 // Range stage for the fused path (CW/executeCFAR.m:45-75): one (grid-stride) thread per velocity hit of
 // this chunk; elects the first maximum among the passing cells of {r-1,r,r+1}, de-duplicates through the
 // per-column velocity-hit masks, appends the 2-D record to the global list and moves the velocity record
 // from the per-slot scratch list to the global one.  The last block to finish re-arms the slot counters.
+template <int REF>
 __global__ void cfar_r64_kernel(const float* __restrict__ rdm, const CfarParams p, float t_r,
                                 const rb200_det* __restrict__ slot_v, int* __restrict__ slot_count,
                                 rb200_det* __restrict__ dets_v, rb200_det* __restrict__ dets_2d, int* __restrict__ gcount,
@@ -176,24 +215,24 @@ __global__ void cfar_r64_kernel(const float* __restrict__ rdm, const CfarParams 
         rb200_det h = slot_v[i];
         if (!p.range_stage) h.kind = RB200_DET_V | RB200_DET_2D;   // executeCFAR.m:91: the final matrix IS the velocity matrix
         {
-            const int slot = atomicAdd(&gcount[0], 1);
+            const int slot = warp_agg_slot(&gcount[0]);
             if (slot < p.max_det) dets_v[slot] = h;
         }
         if (!p.range_stage) continue;
         const int slab = (int)(h.cpi - p.cpi0) * p.n_lanes + h.lane;
         const int v = h.v, r = (int)h.r;
         const float* row = rdm + ((size_t)slab * p.V + v) * p.R;
-        const int c = cfar_elect_f32(row, r, p, t_r, err_flag);
+        const int c = cfar_elect_f32<REF>(row, r, p, t_r, err_flag);
         if (c < 0) continue;
         const unsigned long long* cm = colmask + (size_t)slab * cols_ld;
         bool owner = true;
         for (int rr = c - 1; rr < r && owner; ++rr) {
             if (rr < 0) continue;
             if (!((cm[rr] >> v) & 1ull)) continue;
-            if (cfar_elect_f32(row, rr, p, t_r, nullptr) == c) owner = false;
+            if (cfar_elect_f32<REF>(row, rr, p, t_r, nullptr) == c) owner = false;
         }
         if (!owner) continue;
-        const int slot = atomicAdd(&gcount[1], 1);
+        const int slot = warp_agg_slot(&gcount[1]);
         if (slot < p.max_det) {
             rb200_det d;
             d.cpi = h.cpi;
@@ -250,8 +289,12 @@ cudaError_t launch_mtd64_tma(const Mtd64Params& p, int n_slabs, int n_sms, int c
 cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, const void* slot_v, int* slot_count, void* dets_v,
                             void* dets_2d, int* gcount, const unsigned long long* colmask, int cols_ld, int* err_flag, int n_blocks,
                             cudaStream_t st) {
-    cfar_r64_kernel<<<n_blocks, 128, 0, st>>>(rdm, p, t_r, (const rb200_det*)slot_v, slot_count, (rb200_det*)dets_v,
-                                              (rb200_det*)dets_2d, gcount, colmask, cols_ld, err_flag);
+    if (p.ref_r == 5)
+        cfar_r64_kernel<5><<<n_blocks, 128, 0, st>>>(rdm, p, t_r, (const rb200_det*)slot_v, slot_count, (rb200_det*)dets_v,
+                                                     (rb200_det*)dets_2d, gcount, colmask, cols_ld, err_flag);
+    else
+        cfar_r64_kernel<0><<<n_blocks, 128, 0, st>>>(rdm, p, t_r, (const rb200_det*)slot_v, slot_count, (rb200_det*)dets_v,
+                                                     (rb200_det*)dets_2d, gcount, colmask, cols_ld, err_flag);
     return cudaGetLastError();
 }
 
