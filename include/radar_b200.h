@@ -282,6 +282,14 @@ int rb200_mtd_produce_windows_z(rb200_ctx* ctx, const double* echo_re, const dou
 int rb200_unpack_dbf24(rb200_ctx* ctx, const uint8_t* bytes, int n_prt, int n_samples, int n_channels,
                        float* out_ri, int* n_columns);
 
+/* f1 (batched): the whole chain on DBF-type frames.  payload = n_cpi x n_prt PRT payloads exactly as they sit in the
+ * capture file (FrameDataRead_xzr.m:111-119: n_range rows of 6*n_ch + padding bytes, each PRT padded to 64 B); the
+ * complex columns the reference keeps (:130-135,163) become the cfg.n_lanes lanes of the chain (n_lanes must equal
+ * that column count, e.g. n_ch = 13 -> 13 lanes).  Everything else as rb200_chain_i16.                          */
+int rb200_chain_dbf24(rb200_ctx* ctx, const uint8_t* payload, int n_ch, int n_cpi, float* rdm_out, rb200_det* dets, int* n_det,
+                      void* stream);
+
+
 #ifdef __cplusplus
 }
 #endif

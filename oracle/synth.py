@@ -151,3 +151,25 @@ S1_CFAR = dict(refR=5, saveR=7, T_R=5.0, methR=0, refV=5, saveV=7, T_V=5.0, meth
 def cfar_tuple(d):
     return (d["refR"], d["saveR"], d["T_R"], d["methR"], d["refV"], d["saveV"], d["T_V"], d["methV"],
             d["n0"], d["rflag"])
+
+
+def to_dbf24(lanes, channel_num):
+    """Encode integer-valued complex lanes [prt][range][col] as DBF-type PRT payloads (uint8 [prt][bytes]) the way
+    FrameDataRead_xzr.m:111-119,130-135,163 expects them: rows of 6*channel_num + pad bytes, 3-byte little-endian
+    two's-complement words I0 Q0 I1 Q1 ..., each PRT padded to a multiple of 64 bytes."""
+    from . import mcode
+    lanes = np.asarray(lanes)
+    n_prt, n, ncol = lanes.shape
+    sig, pad, osp = mcode.dbf24_payload_size(n, channel_num)
+    W = channel_num * 6 + osp
+    assert ncol * 6 <= W
+    out = np.zeros((n_prt, sig + pad), dtype=np.uint8)
+    rows = out[:, :sig].reshape(n_prt, n, W)
+    for col in range(ncol):
+        for part, val in ((0, lanes[:, :, col].real), (1, lanes[:, :, col].imag)):
+            w = np.round(val).astype(np.int64) & 0xFFFFFF
+            o = col * 6 + part * 3
+            rows[:, :, o] = w & 0xFF
+            rows[:, :, o + 1] = (w >> 8) & 0xFF
+            rows[:, :, o + 2] = (w >> 16) & 0xFF
+    return out

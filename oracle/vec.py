@@ -328,6 +328,11 @@ def chain(raw, n_cpi, P, R, C, plan, cfar, beta=8.0, zero_div=150, stc=None, mti
     x = unpack_wire(raw, n_cpi, P, R, C)
     if dbf is not None:
         x = dbf_weighting(x, dbf)
+    return chain_lanes(x, plan, cfar, beta=beta, zero_div=zero_div, stc=stc, mti_lag=mti_lag, near_tol=near_tol)
+
+
+def chain_lanes(x, plan, cfar, beta=8.0, zero_div=150, stc=None, mti_lag=0, near_tol=None):
+    """The chain downstream of the unpack, on complex lanes x[cpi, lane, prt, range] (e.g. decoded DBF-type beams)."""
     if stc is not None:
         x = istc(x, stc)
     if plan[0] == "single":

@@ -259,6 +259,19 @@ class Context:
             self._ck(st)
         return rdm, dets[: min(n.value, c.max_det)].copy(), n.value
 
+    def chain_dbf24(self, payload, n_ch, n_cpi, want_rdm=True, allow_overflow=False):
+        """Chain on DBF-type 24-bit PRT payloads (uint8, n_cpi x n_prt x padded PRT bytes); lanes = decoded complex columns."""
+        c = self.cfg
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        rdm = np.zeros((n_cpi, c.n_lanes, c.n_prt, c.n_range), dtype=np.float32) if want_rdm else None
+        dets = np.zeros(c.max_det, dtype=B.DET_DTYPE)
+        n = C.c_int(0)
+        st = self._lib.rb200_chain_dbf24(self._h, payload.ctypes.data, int(n_ch), n_cpi, rdm.ctypes.data if want_rdm else None,
+                                         dets.ctypes.data, C.byref(n), None)
+        if not (st == B.ERR_OVERFLOW and allow_overflow):
+            self._ck(st)
+        return rdm, dets[: min(n.value, c.max_det)].copy(), n.value
+
     def chain_ptr(self, raw_ptr, n_cpi, rdm_ptr, dets_ptr, stream=None):
         """Raw-pointer chain call (host or device addresses as ints); returns (status, n_det)."""
         n = C.c_int(0)

@@ -1168,10 +1168,8 @@ extern "C" int rb200_unpack_ddc_i16(rb200_ctx* c, const int16_t* raw, int n_cpi,
     return RB200_OK;
 }
 
-extern "C" int rb200_unpack_dbf24(rb200_ctx* c, const uint8_t* bytes, int n_prt, int n, int n_ch, float* out_ri, int* n_columns) {
-    if (!c || !bytes || !out_ri || n_prt < 1 || n < 1 || n_ch < 1) return fail(c, RB200_ERR_ARG, "unpack_dbf24: bad argument");
-    cudaSetDevice(c->device);
-    c->launches = 0;
+// geometry of a DBF-type PRT payload: row width W (bytes per range sample), padded PRT size, complex columns produced
+static int dbf24_geometry(rb200_ctx* c, int n, int n_ch, int* W_out, size_t* prt_bytes_out, int* ncol_out) {
     const int osp = 8 - (6 * n_ch) % 8;                                   // FrameDataRead_xzr.m:111
     const int W = 6 * n_ch + osp;
     const size_t sig = (size_t)n * W;                                     // :112
@@ -1179,7 +1177,20 @@ extern "C" int rb200_unpack_dbf24(rb200_ctx* c, const uint8_t* bytes, int n_prt,
     // column counts of 1:3:end-3, 2:3:end-2, 3:3:end must agree (MATLAB would raise otherwise)
     const int n1 = (W - 3 >= 1) ? (W - 3 - 1) / 3 + 1 : 0, n2 = (W - 2 >= 2) ? (W - 2 - 2) / 3 + 1 : 0, n3 = (W >= 3) ? (W - 3) / 3 + 1 : 0;
     if (n1 != n2 || n2 != n3 || (n1 % 2)) return fail(c, RB200_ERR_DIM_MISMATCH, "frameDataRead: arrays have incompatible sizes (24-bit word slicing)");
-    const int ncol = n1 / 2;
+    *W_out = W;
+    *prt_bytes_out = prt_bytes;
+    *ncol_out = n1 / 2;
+    return RB200_OK;
+}
+
+extern "C" int rb200_unpack_dbf24(rb200_ctx* c, const uint8_t* bytes, int n_prt, int n, int n_ch, float* out_ri, int* n_columns) {
+    if (!c || !bytes || !out_ri || n_prt < 1 || n < 1 || n_ch < 1) return fail(c, RB200_ERR_ARG, "unpack_dbf24: bad argument");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    int W, ncol;
+    size_t prt_bytes;
+    int grc = dbf24_geometry(c, n, n_ch, &W, &prt_bytes, &ncol);
+    if (grc) return grc;
     if (n_columns) *n_columns = ncol;
     const size_t in_bytes = prt_bytes * n_prt, out_elems = (size_t)ncol * n_prt * n;
     CK(c, c->raw.ensure(in_bytes));
@@ -1256,17 +1267,29 @@ static int chunk_size(const rb200_ctx* c) {
 
 // raw_host / rdm_host (optional): host buffers staged chunk by chunk on the chunk's own stream, so the H2D copy
 // of chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i (three slots, two copy engines).
+// dbf24_ch > 0: the input is the DBF-type 24-bit payload of `dbf24_ch` channels per PRT (row f1, FrameDataRead_xzr.m:111-119,
+// 130-135,163) whose complex columns are the cfg.n_lanes lanes of the chain; raw_* then point at bytes.
 static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float* rdm_dev, cudaStream_t st,
-                         const int16_t* raw_host = nullptr, float* rdm_host = nullptr) {
+                         const int16_t* raw_host = nullptr, float* rdm_host = nullptr, int dbf24_ch = 0) {
     const rb200_config& k = c->cfg;
     const int P = k.n_prt, R = k.n_range;
     const int Cin = k.n_lanes;                                   // channels interleaved in the wire format
     const int C = c->dbf_beams ? c->dbf_beams : Cin;             // lanes downstream of the (optional) beam former
+    int d24_W = 0, d24_ncol = 0;
+    size_t d24_prt_bytes = 0;
+    if (dbf24_ch > 0) {
+        if (c->dbf_beams) return fail(c, RB200_ERR_ARG, "chain_dbf24: DBF-type data is already beam-formed (clear rb200_set_dbf first)");
+        int grc = dbf24_geometry(c, R, dbf24_ch, &d24_W, &d24_prt_bytes, &d24_ncol);
+        if (grc) return grc;
+        if (d24_ncol != C) return fail(c, RB200_ERR_DIM_MISMATCH, "chain_dbf24: the payload's complex column count differs from n_lanes");
+    }
     if (n_cpi < 1 || n_cpi > k.max_cpi) return fail(c, RB200_ERR_ARG, "chain: n_cpi must be in 1..max_cpi");
     if (k.cfar_n0 < 0) return fail(c, RB200_ERR_INDEX, "executeCFAR: Index in position 1 exceeds array bounds (MTD_0_num < 0)");
     const int G = chunk_size(c);
     const size_t cpi_cells = (size_t)P * R * C;
     const size_t raw_cells = (size_t)P * R * Cin;
+    const size_t raw_cpi_bytes = dbf24_ch > 0 ? (size_t)P * d24_prt_bytes : raw_cells * 4;   // input bytes of one CPI
+    const bool planar_in = c->dbf_beams > 0 || dbf24_ch > 0;    // a first kernel produces planar [cpi][lane][prt][range] lines
     const int Rw = (R + 31) / 32;
     CK(c, c->dets_v.ensure((size_t)k.max_det * sizeof(rb200_det)));
     CK(c, c->dets_2d.ensure((size_t)k.max_det * sizeof(rb200_det)));
@@ -1294,7 +1317,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     c->last_was_mega = false;
     // ---- fused persistent kernel for the whole batch (chain64_kernel.cu): device-resident input and output, 16 channels,
     //      one 256-sample tile class covering the whole PRT
-    if (fused && raw_dev && rdm_dev && !raw_host && !rdm_host && C == 16 && !c->dbf_beams && c->plan.valid && c->plan.classes.size() == 1 &&
+    if (fused && raw_dev && rdm_dev && !raw_host && !rdm_host && C == 16 && !planar_in && c->plan.valid && c->plan.classes.size() == 1 &&
         c->plan.classes[0].nt == 256 && c->plan.max_in_end <= R && c->plan.max_out_end <= R && (reinterpret_cast<uintptr_t>(raw_dev) & 15) == 0 &&
         getenv("RB200_MEGA")) {      // opt-in: measured slower than the slot pipeline on B200 (profiles/README.md)
         bool direct = false, covered = true;
@@ -1401,8 +1424,8 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         CK(c, c->vmask.ensure((size_t)G * C * P * Rw * sizeof(uint32_t)));
     }
     for (int i = 0; i < n_slots; ++i) {
-        if (raw_host) CK(c, c->slots[i].raw.ensure((size_t)G * raw_cells * 4));
-        if (c->dbf_beams) CK(c, c->slots[i].beams.ensure((size_t)G * cpi_cells * sizeof(float2)));
+        if (raw_host) CK(c, c->slots[i].raw.ensure((size_t)G * raw_cpi_bytes));
+        if (planar_in) CK(c, c->slots[i].beams.ensure((size_t)G * cpi_cells * sizeof(float2)));
         if (rdm_host) CK(c, c->slots[i].rdm.ensure((size_t)G * cpi_cells * sizeof(float)));
     }
     CK(c, cudaEventRecord(c->ev0, st));
@@ -1415,9 +1438,11 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         const int g = std::min(G, n_cpi - c0);
         rb200_ctx::Slot& sl = c->slots[chunk_idx % n_slots];
         cudaStream_t cs = (fused && n_slots > 1) ? sl.stream : st;
-        const int16_t* raw_chunk = raw_dev ? raw_dev + (size_t)c0 * raw_cells * 2 : nullptr;
+        const int16_t* raw_chunk =
+            raw_dev ? reinterpret_cast<const int16_t*>(reinterpret_cast<const uint8_t*>(raw_dev) + (size_t)c0 * raw_cpi_bytes) : nullptr;
         if (raw_host) {
-            CK(c, cudaMemcpyAsync(sl.raw.p, raw_host + (size_t)c0 * raw_cells * 2, (size_t)g * raw_cells * 4, cudaMemcpyHostToDevice, cs));
+            CK(c, cudaMemcpyAsync(sl.raw.p, reinterpret_cast<const uint8_t*>(raw_host) + (size_t)c0 * raw_cpi_bytes, (size_t)g * raw_cpi_bytes,
+                                  cudaMemcpyHostToDevice, cs));
             raw_chunk = sl.raw.as<int16_t>();
         }
         float* rdm_chunk = rdm_host ? sl.rdm.as<float>() : (rdm_dev ? rdm_base + (size_t)c0 * cpi_cells : rdm_base);
@@ -1425,7 +1450,15 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         const bool timed = c->stage_timing && c->stage_used + 4 <= 65536;
         if (timed) { stage_event(c, cs); c->stage_cpis.push_back(g); }
         int rc;
-        if (c->dbf_beams) {
+        if (dbf24_ch > 0) {
+            // f1: 24-bit DBF-type payload -> planar [cpi][beam][prt][range], one launch per CPI of the chunk
+            for (int q = 0; q < g; ++q) {
+                CK(c, launch_unpack_dbf24(reinterpret_cast<const uint8_t*>(raw_chunk) + (size_t)q * raw_cpi_bytes,
+                                          sl.beams.as<float2>() + (size_t)q * cpi_cells, P, R, C, d24_W, d24_prt_bytes, cs));
+                c->launches++;
+            }
+            rc = run_pc(c, c->plan, false, sl.beams.p, pc_buf, R, R, 1, P, 0, g * C * P, c->gain_n ? c->gain.as<float>() : nullptr, cs);
+        } else if (c->dbf_beams) {
             // f1: beams = sig_C * W.' fused with the unpack, then planar pulse compression over cpi x beam x PRT lines
             CK(c, launch_dbf(raw_chunk, sl.beams.as<float2>(), c->dbf_w.as<float2>(), C, Cin, g * P, P, R, cs));
             c->launches++;
@@ -1537,6 +1570,22 @@ extern "C" int rb200_chain_i16(rb200_ctx* c, const int16_t* raw, int n_cpi, floa
     const bool rdm_on_dev = rdm_out && is_device_ptr(rdm_out);
     int rc = chain_enqueue(c, raw_on_dev ? raw : nullptr, n_cpi, rdm_on_dev ? rdm_out : nullptr, st,
                            raw_on_dev ? nullptr : raw, (rdm_out && !rdm_on_dev) ? rdm_out : nullptr);
+    if (rc) return rc;
+    return chain_fetch(c, dets, dets && is_device_ptr(dets), n_det, st);
+}
+
+extern "C" int rb200_chain_dbf24(rb200_ctx* c, const uint8_t* payload, int n_ch, int n_cpi, float* rdm_out, rb200_det* dets, int* n_det,
+                                 void* stream) {
+    if (!c || !payload || n_ch < 1) return fail(c, RB200_ERR_ARG, "chain_dbf24: bad argument");
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const rb200_config& k = c->cfg;
+    if (n_cpi < 1 || n_cpi > k.max_cpi) return fail(c, RB200_ERR_ARG, "chain: n_cpi must be in 1..max_cpi");
+    const bool raw_on_dev = is_device_ptr(payload);
+    const bool rdm_on_dev = rdm_out && is_device_ptr(rdm_out);
+    const int16_t* raw = reinterpret_cast<const int16_t*>(payload);
+    int rc = chain_enqueue(c, raw_on_dev ? raw : nullptr, n_cpi, rdm_on_dev ? rdm_out : nullptr, st, raw_on_dev ? nullptr : raw,
+                           (rdm_out && !rdm_on_dev) ? rdm_out : nullptr, n_ch);
     if (rc) return rc;
     return chain_fetch(c, dets, dets && is_device_ptr(dets), n_det, st);
 }

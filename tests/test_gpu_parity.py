@@ -668,3 +668,30 @@ def test_dmx_argument_errors(lib):
             ctx.dmx_process(left, right, 10, mcode.FILTER_COEF_INT, mf[:20], 256, np.ones(16), 8, 0)
         with pytest.raises(lib.RadarB200Error):       # blanking wider than the Doppler axis
             ctx.dmx_process(left, right, 10, mcode.FILTER_COEF_INT, mf, 256, win, 16, 9)
+
+
+@pytest.mark.parametrize("P,R,n_ch,B,chunk", [(64, 512, 13, 3, 2), (256, 300, 4, 1, 1)])
+def test_chain_on_dbf24_payloads(lib, P, R, n_ch, B, chunk):
+    """f1 (batched): DBF-type 24-bit frames straight into the chain; lanes = the complex columns the reference keeps."""
+    ref = mcode.load_ref("refDBFDataMF1")
+    rng = np.random.default_rng(P + n_ch)
+    sig, pad, osp = mcode.dbf24_payload_size(R, n_ch)
+    ncol = ((n_ch * 6 + osp) // 3) // 2
+    lanes = np.round(rng.normal(0, 3000, (B, P, R, ncol))) + 1j * np.round(rng.normal(0, 3000, (B, P, R, ncol)))
+    for b in range(B):
+        for col in range(ncol):
+            r0, dop = 40 + 17 * col + 5 * b, 0.07 * (col + 1) - 0.3
+            echo = (30000.0 / np.abs(ref).max()) * ref[None, :] * np.exp(2j * np.pi * dop * np.arange(P))[:, None]
+            lanes[b, :, r0:r0 + ref.size, col] += np.round(echo.real) + 1j * np.round(echo.imag)
+    lanes[0, 0, 0, 0] = -8388607 + 8388607j                                   # extreme codes survive the round trip
+    payload = np.stack([synth.to_dbf24(lanes[b], n_ch) for b in range(B)])       # [cpi][prt][bytes]
+    decoded = np.stack([np.stack([mcode.unpack_dbf24(payload[b, p], R, n_ch) for p in range(P)]) for b in range(B)])
+    assert np.array_equal(decoded, lanes)
+    cfar = (5, 7, 6.0, 0, 5, 7, 6.0, 0, 0, 1)
+    out = vec.chain_lanes(lanes.transpose(0, 3, 1, 2), ("single", ref), cfar, near_tol=RTOL)
+    with _chain_ctx(lib, P, R, ncol, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=chunk, max_det=1 << 20) as ctx:
+        rdm, dets, n = ctx.chain_dbf24(payload, n_ch, B)
+        with pytest.raises(lib.RadarB200Error):                                 # column count must match n_lanes
+            ctx.chain_dbf24(payload, n_ch + 3, B)
+    _close(rdm, out["rdm"])
+    _compare_flags(dets, out, B, ncol, P, R, lib)
