@@ -1253,7 +1253,7 @@ extern "C" int rb200_motion_para_measure_d(rb200_ctx* c, const double* mtd_sum, 
     return fetch_errflag(c, "motionParaMeasure: Index exceeds array bounds");
 }
 
-static int chunk_size(const rb200_ctx* c) {
+static int chunk_size(const rb200_ctx* c, bool host_staged = false) {
     const char* env = getenv("RB200_CHUNK");
     int g = env ? atoi(env) : c->cfg.chunk_cpi;
     if (g <= 0) {
@@ -1261,6 +1261,9 @@ static int chunk_size(const rb200_ctx* c) {
         // 4 CPIs per chunk and the PC intermediate is not L2-resident at any practical chunk size (profiles/README.md)
         const double per_cpi = (double)c->cfg.n_prt * c->cfg.n_range * c->cfg.n_lanes * 16.0;
         g = (int)std::floor(540e6 / per_cpi);
+        // host buffers: the call is PCIe-bound and the first H2D / last D2H of a call cannot overlap anything, so halve
+        // the chunk (measured: 2.63 k -> 2.71 k CPI/s end to end; 49 GB/s each way is the box's full-duplex ceiling)
+        if (host_staged) g = std::max(1, g / 2);
     }
     return std::max(1, std::min(g, c->cfg.max_cpi));
 }
@@ -1285,7 +1288,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     }
     if (n_cpi < 1 || n_cpi > k.max_cpi) return fail(c, RB200_ERR_ARG, "chain: n_cpi must be in 1..max_cpi");
     if (k.cfar_n0 < 0) return fail(c, RB200_ERR_INDEX, "executeCFAR: Index in position 1 exceeds array bounds (MTD_0_num < 0)");
-    const int G = chunk_size(c);
+    const int G = chunk_size(c, raw_host != nullptr || rdm_host != nullptr);
     const size_t cpi_cells = (size_t)P * R * C;
     const size_t raw_cells = (size_t)P * R * Cin;
     const size_t raw_cpi_bytes = dbf24_ch > 0 ? (size_t)P * d24_prt_bytes : raw_cells * 4;   // input bytes of one CPI
