@@ -88,6 +88,55 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class NvmlSampler(threading.Thread):
+    """SM clock and clock-event reasons read through NVML about every millisecond, only while `active` is set (the
+    device-timed region); falls back to the nvidia-smi sampler when NVML is unavailable."""
+
+    def __init__(self, torch_device):
+        super().__init__(daemon=True)
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        import torch
+        handle = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(torch_device).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(torch_device.index or 0)
+        self.h = handle
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        self.active = threading.Event()
+        self.done = threading.Event()
+        self.sm, self.bits = [], 0
+
+    def run(self):
+        nv = self.nv
+        while not self.done.is_set():
+            if self.active.is_set():
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    pass
+            time.sleep(0.001)
+
+    def stop(self):
+        self.done.set()
+        self.join(timeout=2)
+
+    def summary(self):
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                 ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown))
+        reasons = sorted(n for n, bit in names if self.bits & bit)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": 0, "source": "nvml"}
+        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.sm), "source": "nvml, ~1 ms cadence, device-timed region only"}
+
+
 # --------------------------------------------------------------------------------------------------
 def cpu_reference_rate(n_cpis, first_cpi=0, workers=None):
     """Time the oracle port of the reference chain (vectorised NumPy/SciPy double precision, all host
@@ -209,17 +258,28 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.25)
+    sampler, nvml = None, None
+    if rank == 0:
+        try:
+            nvml = NvmlSampler(dev)
+            nvml.start()
+        except Exception:
+            nvml = None
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            time.sleep(0.25)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if nvml:
+        nvml.active.set()
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
     e1.record(stream)
     barrier()
+    if nvml:
+        nvml.active.clear()
+        nvml.stop()
     ms = e0.elapsed_time(e1)
     launches_per_step = ctx.last_launch_count()
     dets, n_det = ctx.chain_fetch(allow_overflow=True)
@@ -308,7 +368,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": B * CELLS * 4 + 16 * min(n_e2e, args.max_det), "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
             "detections_per_step": n_det, "gather_ms": gather_ms, "detections_gathered": n_gathered,
-            "clocks": sampler.summary() if sampler else None,
+            "clocks": nvml.summary() if nvml else (sampler.summary() if sampler else None),
         }
         if world == 1 and not args.no_cpu_baseline:
             cps, dt = cpu_reference_rate(args.cpu_cpis)
