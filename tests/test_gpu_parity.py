@@ -695,3 +695,25 @@ def test_chain_on_dbf24_payloads(lib, P, R, n_ch, B, chunk):
             ctx.chain_dbf24(payload, n_ch + 3, B)
     _close(rdm, out["rdm"])
     _compare_flags(dets, out, B, ncol, P, R, lib)
+
+
+def test_chain_S5_full_size_two_lanes_against_oracle(lib):
+    """Configuration S5 at BASELINE's full size (256 PRT x 16384 range x 16 lanes, refDBFDataMF1, iSTC + MTI): the oracle
+    is run on two of the sixteen lanes (all range cells) and compared cell by cell; all lanes obey the 0-v mask."""
+    P, R, C = 256, 16384, 16
+    ref = mcode.load_ref("refDBFDataMF1")
+    raw, _ = synth.s3_cpi(0, P=P, R=R, C=C, ref=ref, seed0=5000, r_lo=100, r_hi=R - 200, exclude=(-3, -2, -1, 0, 1, 2, 3))
+    raw = raw[None]
+    stc = synth.s5_stc_curve()
+    cfar = synth.cfar_tuple(synth.S5_CFAR)
+    with _chain_ctx(lib, P, R, C, 1, lib.waveforms.segments_single(R, ref), cfar, mti_lag=30, max_det=1 << 20) as ctx:
+        ctx.set_stc(stc)
+        rdm, dets, n = ctx.chain(raw, 1)
+    assert np.all(rdm[:, :, 125:130, :] == 0) and n > 0
+    for lane in (0, 15):
+        sub = np.ascontiguousarray(raw[:, :, :, lane:lane + 1, :])
+        out = vec.chain(sub, 1, P, R, 1, ("single", ref), cfar, stc=stc, mti_lag=30, near_tol=RTOL)
+        _close(rdm[:, lane:lane + 1], out["rdm"])
+        d = dets[dets["lane"] == lane].copy()
+        d["lane"] = 0
+        _compare_flags(d, out, 1, 1, P, R, lib)
