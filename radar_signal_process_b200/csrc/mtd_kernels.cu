@@ -51,28 +51,30 @@ mtd_fast_kernel(const MtdParams p) {
     const int slab = blockIdx.y;
     const int r = blockIdx.x * TR + rl;
     const bool ok = r < p.cols;
-    // 32-bit element offsets inside one slab (P * in_ld < 2^31 is checked by the launcher)
-    const float2* col = p.in + (size_t)slab * P * p.in_ld + (ok ? r : 0) + u * p.in_ld;
-    const int step = R * p.in_ld;
+    // one 64-bit byte address per thread, then a constant byte stride: pulse u + j*R sits j*stepb bytes further on
+    // (kept as integers so that the compiler steps the address instead of re-deriving it from an element index)
+    unsigned long long a0 = reinterpret_cast<unsigned long long>(p.in + (size_t)slab * P * p.in_ld + (ok ? r : 0) + (size_t)u * p.in_ld);
+    const unsigned long long stepb = (unsigned long long)R * p.in_ld * sizeof(float2);
 
     float2 v[R];
     if (MTI) {
         // x[p + lag] - x[p], the last `lag` pulses are zero (MP/fun_Process_MTI.m:20-22)
-        const int lag_off = p.mti_lag * p.in_ld;
+        unsigned long long a1 = a0 + (unsigned long long)p.mti_lag * p.in_ld * sizeof(float2);
+        const int last = P - p.mti_lag - u;            // pulse u + j*R is kept iff j*R < last
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            const int prt = u + j * R;
             float2 x = make_float2(0.f, 0.f);
-            if (prt < P - p.mti_lag) {
-                const float2 a = __ldg(col + j * step + lag_off);
-                const float2 b = __ldg(col + j * step);
-                x = make_float2(a.x - b.x, a.y - b.y);
-            }
-            v[j] = cscale(x, __ldg(p.window + prt));
+            if (j * R < last) x = csub(__ldg(reinterpret_cast<const float2*>(a1)), __ldg(reinterpret_cast<const float2*>(a0)));
+            v[j] = cscale(x, __ldg(p.window + u + j * R));
+            a0 += stepb;
+            a1 += stepb;
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < R; ++j) v[j] = cscale(__ldg(col + j * step), __ldg(p.window + u + j * R));
+        for (int j = 0; j < R; ++j) {
+            v[j] = cscale(__ldg(reinterpret_cast<const float2*>(a0)), __ldg(p.window + u + j * R));
+            a0 += stepb;
+        }
     }
     Dft<R, -1>::run(v);
 #pragma unroll
@@ -83,34 +85,33 @@ mtd_fast_kernel(const MtdParams p) {
 #pragma unroll
     for (int j = 0; j < R; ++j) v[j] = sm[(u * R + j) * TR + rl];
     Dft<R, -1>::run(v);
-    if (CF == 0) {
-        if (!ok) return;
-        float* out = p.out + (size_t)slab * P * p.out_ld + r;
-#pragma unroll
-        for (int k1 = 0; k1 < R; ++k1) {
-            const int row = (u + R * k1 + P / 2) & (P - 1);     // Doppler bin u + R*k1 after fftshift
-            float mag = mtd_fast_sqrt(v[k1].x * v[k1].x + v[k1].y * v[k1].y);
-            if (row >= p.zv_lo && row <= p.zv_hi) mag = 0.f;
-            out[row * p.out_ld] = mag;
-        }
-        return;
-    }
+    // Output rows of this thread after fftshift: Doppler bin u + R*k1 lands on row u + P/2 + R*k1 for k1 < R/2 and on
+    // row u + R*(k1 - R/2) for the rest, i.e. two runs of constant stride -> stepped byte addresses, immediate offsets.
+    // zrow0: first row >= zv_lo that is congruent to u (mod R); rows of this thread are zeroed iff zrow0 <= zv_hi
+    // (u is warp-uniform, so the common "nothing to zero" case skips every per-row test).
+    const int zrow0 = p.zv_lo + ((u - p.zv_lo) % R + R) % R;
+    const bool zany = p.zv_lo <= p.zv_hi && zrow0 <= p.zv_hi;
+    const unsigned long long rowb = (unsigned long long)p.out_ld * sizeof(float);
+    const unsigned long long o_lo = reinterpret_cast<unsigned long long>(p.out + (size_t)slab * P * p.out_ld + r) + u * rowb;   // row u
+    const unsigned long long o_hi = o_lo + (P / 2) * rowb;                                                                     // row u + P/2
+    const unsigned long long ostep = R * rowb;
     // The magnitude tile [P][TR] re-uses the exchange buffer (2*P*TR floats) once everybody has read it; it sits
     // P/2 rows into the buffer so that window reads up to P/2 rows outside the tile stay inside the allocation
     // (those values are never used: the edge rule replaces the side that does not fit).
     float* mag_sm = reinterpret_cast<float*>(sm) + (P / 2) * TR;
-    __syncthreads();
-    {
-        float* out = p.out + (size_t)slab * P * p.out_ld + r;
+    if (CF != 0) __syncthreads();
+    float* mag_u = mag_sm + u * TR + rl;               // row u of this thread's column
+    if (CF == 0 && !ok) return;
 #pragma unroll
-        for (int k1 = 0; k1 < R; ++k1) {
-            const int row = (u + R * k1 + P / 2) & (P - 1);
-            float mag = mtd_fast_sqrt(v[k1].x * v[k1].x + v[k1].y * v[k1].y);
-            if (row >= p.zv_lo && row <= p.zv_hi) mag = 0.f;
-            if (ok) out[row * p.out_ld] = mag;
-            mag_sm[row * TR + rl] = mag;
-        }
+    for (int k1 = 0; k1 < R; ++k1) {
+        const int roff = k1 < R / 2 ? P / 2 + R * k1 : R * (k1 - R / 2);     // row - u, compile-time
+        float mag = mtd_fast_sqrt(v[k1].x * v[k1].x + v[k1].y * v[k1].y);
+        if (zany && u + roff >= p.zv_lo && u + roff <= p.zv_hi) mag = 0.f;
+        const unsigned long long oa = (k1 < R / 2 ? o_hi + k1 * ostep : o_lo + (k1 - R / 2) * ostep);
+        if (ok) *reinterpret_cast<float*>(oa) = mag;
+        if (CF != 0) mag_u[roff * TR] = mag;
     }
+    if (CF == 0) return;
     // ---- fused velocity-axis CA-CFAR (CW/executeCFAR.m:28, CW/Function_CFAR1D_sub.m:17-69) on the tile ----
     // Thread (u, rl) decides rows [u*R, (u+1)*R) of column rl; the reference windows come from shared memory.
     __syncthreads();

@@ -172,6 +172,7 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
     float2* tw_sm = reinterpret_cast<float2*>(smem_raw + FFT_BYTES + 2 * RAW_INTS * 4);
     float2* h_sm = tw_sm + TW_N;
     __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ float gain_sm[GAIN ? 2 * NT : 1];       // iSTC gains of the current / next tile (blockDim.x == NT threads fill it)
 
     const int t = threadIdx.x;
     const int lane = t % LT;
@@ -183,6 +184,15 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
     }
     for (int i = t; i < TW_N; i += blockDim.x) tw_sm[i] = __ldg(p.tw + i);
     for (int i = t; i < h_entries; i += blockDim.x) h_sm[i] = __ldg(p.hperm + i);
+    // gains of tile sample t of `item` (MP/fun_iSTC.m:14); samples outside the segment get 0 (their raw value is 0 too)
+    auto stage_gain = [&](int item, int buf) {
+        const int g = item / n_tiles;
+        const int2 tile = __ldg(&p.tiles[item - g * n_tiles]);
+        const PcSegDev& sg = p.segs[tile.x];
+        const int rs = tile.y * sg.V - sg.pre + t;
+        gain_sm[GAIN ? buf * NT + t : 0] = (rs >= 0 && rs < sg.in_len) ? __ldg(p.gain + sg.in_start + rs) : 0.f;
+    };
+    if (GAIN && (int)blockIdx.x < n_items) stage_gain(blockIdx.x, 0);
     __syncthreads();
 
     // thread 0: start the bulk copy of an item's valid input span into staging buffer `buf`
@@ -212,16 +222,6 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
         const PcSegDev& sg = p.segs[tile.x];
         const int in_off = tile.y * sg.V - sg.pre;
 
-        // iSTC gains of this thread's samples (MP/fun_iSTC.m:14) are fetched before waiting for the raw tile, so their
-        // global-load latency hides behind the TMA wait instead of stalling the first butterfly
-        float gv[GAIN ? R : 1];
-        if (GAIN) {
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const int rs = in_off + u + j * NB;
-                gv[GAIN ? j : 0] = (rs >= 0 && rs < sg.in_len) ? __ldg(p.gain + sg.in_start + rs) : 0.f;
-            }
-        }
         mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
         float2 v[R];
         {
@@ -244,9 +244,10 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
                     v[j].y = (float)(w >> 16);
                 }
             }
-            if (GAIN) {
+            if (GAIN) {      // staged one item ahead (below), so no global-load latency sits in front of the first butterfly
+                const float* gs = gain_sm + (GAIN ? buf * NT + u : 0);
 #pragma unroll
-                for (int j = 0; j < R; ++j) v[j] = cscale(v[j], gv[GAIN ? j : 0]);   // samples outside the segment are 0 already
+                for (int j = 0; j < R; ++j) v[j] = cscale(v[j], gs[GAIN ? j * NB : 0]);
             }
         }
         // generic-proxy reads of the staging buffer are ordered before the TMA (async-proxy) refill that thread 0
@@ -256,6 +257,7 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
         {
             const int next = item + gridDim.x;
             if (t == 0 && next < n_items) issue(next, buf ^ 1);
+            if (GAIN && next < n_items) stage_gain(next, buf ^ 1);      // read after the end-of-item barrier
         }
         int out_lane, out_u;
         pc_fft_core<R, S, LT, true>(v, sm, tw_sm, h_sm + sg.h_off, t, lane, u, out_lane, out_u);
