@@ -210,6 +210,21 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch_device):
+    """Pin this process to the CPUs NVML reports as local to its GPU, so that the pinned staging buffers (first touch)
+    and the copy-submitting thread sit on the GPU's own NUMA node; matters for the end-to-end figure at N > 1."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(torch_device).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID((uuid if uuid.startswith("GPU-") else "GPU-" + uuid).encode())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return "nvml cpu affinity (%d cpus)" % len(os.sched_getaffinity(0))
+    except Exception as e:                                    # not fatal: the device-resident figure does not depend on it
+        return "unbound (%s)" % type(e).__name__
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -224,6 +239,7 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -350,7 +366,7 @@ def run_gpu(args):
             "config": {"workload": "S3 synthetic LFM DDC 4096 range x 64 PRT x 16 lanes, plan single (refDDCDataMF1), CFAR 5/7/T5/GO",
                        "cpis_per_step_per_gpu": B, "distinct_cpis": min(args.distinct, B), "chunk_cpi": args.chunk,
                        "l2": "inputs larger than L2 (%.0f MiB raw + %.0f MiB RDM per step)" % (B * CELLS * 4 / 2 ** 20, B * CELLS * 4 / 2 ** 20),
-                       "parallelism": "cpi-shard x%d, no hot-path collective" % world},
+                       "parallelism": "cpi-shard x%d, no hot-path collective" % world, "host_binding": numa},
             "hbm_gbs_chain": value / world * ALG_BYTES_PER_CPI / 1e9,
             "hbm_frac_chain": value / world * ALG_BYTES_PER_CPI / 1e9 / peak,
             "roofline": {"bound": "hbm", "kernel": "pc_fft_tma_kernel (K1: int16 unpack + overlap-save pulse compression; 60 % of the chain's device time)",
