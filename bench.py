@@ -210,6 +210,9 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
+ALL_CPUS = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else set()
+
+
 def bind_to_gpu_numa_node(torch_device):
     """Pin this process to the CPUs NVML reports as local to its GPU, so that the pinned staging buffers (first touch)
     and the copy-submitting thread sit on the GPU's own NUMA node; matters for the end-to-end figure at N > 1."""
@@ -387,6 +390,10 @@ def run_gpu(args):
             "clocks": nvml.summary() if nvml else (sampler.summary() if sampler else None),
         }
         if world == 1 and not args.no_cpu_baseline:
+            try:
+                os.sched_setaffinity(0, ALL_CPUS)            # the CPU baseline may use every host core again
+            except Exception:
+                pass
             cps, dt = cpu_reference_rate(args.cpu_cpis)
             loop_cps, loop_dt = cpu_loop_faithful_rate()
             line["cpu_baseline"] = {"value": cps, "unit": "CPI/s", "cores": os.cpu_count() or 1, "kind": "port",
