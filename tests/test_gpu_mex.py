@@ -118,3 +118,24 @@ def test_mex_motionParaMeasure():
     assert np.allclose(rE[:, 0], wr, rtol=1e-11) and np.allclose(vE[:, 0], wv, rtol=1e-11, atol=1e-12) and np.allclose(eE[:, 0], we, rtol=1e-11)
     none = Mex("motionParaMeasure")(s, d, np.zeros((V, R)), *args)
     assert none.size == 0
+
+
+def test_mex_DMX_frame_process():
+    """The DMX script block (FIR short pulse, circular matched filter, zero-padded MTD, sum / difference) through its gateway."""
+    rng = np.random.default_rng(11)
+    P, n_range, n_short, fft_num, mtd_fft, n0 = 48, 566, 62, 512, 64, 2
+    left = np.rint(50 * _rc(rng, P, n_range))
+    right = np.rint(50 * _rc(rng, P, n_range))
+    mf = mcode.dmx_match_filter(mcode.load_ref("refDDCDataMF1"))
+    win = mcode.hamming(P)
+    want = mcode.dmx_frame(left, right, n_short, mcode.FILTER_COEF_INT, mf, fft_num, win, mtd_fft, n0)
+    got = Mex("DMX_frame_process")(left, right, n_short, mcode.FILTER_COEF_INT, mf, fft_num, win.reshape(-1, 1), mtd_fft, n0, nargout=4)
+    assert len(got) == 4
+    for g, w in zip(got, want):
+        _close(g, w)
+    with pytest.raises(MexError) as e:
+        Mex("DMX_frame_process")(left, right[:, :500], n_short, mcode.FILTER_COEF_INT, mf, fft_num, win, mtd_fft, n0, nargout=4)
+    assert e.value.ident == "radar_b200:dmx:dimensionMismatch"
+    with pytest.raises(MexError) as e:
+        Mex("DMX_frame_process")(left, right, n_short, mcode.FILTER_COEF_INT, mf, 500, win, mtd_fft, n0, nargout=4)
+    assert e.value.ident == "radar_b200:dmx:unsupported"
