@@ -32,20 +32,26 @@ def _draw(seed):
     use_stc = rng.random() < 0.3
     chunk = int(rng.integers(1, B + 1))
     ref_name = "refDDCDataMF1" if rng.random() < 0.6 else "refDBFDataMF1"
-    return dict(P=P, C=C, R=R, B=B, cfar=cfar, mti=mti, zdiv=zdiv, stc=use_stc, chunk=chunk, ref=ref_name)
+    lss = bool(rng.random() < 0.3) and R >= 700             # 5-arg segment rule 82 / 242 / rest with the literal pulses
+    return dict(P=P, C=C, R=R, B=B, cfar=cfar, mti=mti, zdiv=zdiv, stc=use_stc, chunk=chunk, ref=ref_name, lss=lss)
 
 
-@pytest.mark.parametrize("seed", range(20))
+@pytest.mark.parametrize("seed", range(28))
 def test_chain_random_configuration(lib, seed):
     k = _draw(seed)
     P, R, C, B = k["P"], k["R"], k["C"], k["B"]
     ref = mcode.load_ref(k["ref"])
     raw, _ = synth.s3_batch(B, P=P, R=R, C=C, ref=ref, n_targets=3, r_lo=20, r_hi=R - 80, seed0=100 * seed)
     stc = synth.s5_stc_curve()[: min(1025, R)] if k["stc"] else None
-    out = vec.chain(raw, B, P, R, C, ("single", ref), k["cfar"], zero_div=k["zdiv"], stc=stc, mti_lag=k["mti"], near_tol=RTOL)
+    if k["lss"]:
+        p2, p3 = mcode.load_pulse_literals()
+        plan, segs = ("lss_mp", p2, p3), lib.waveforms.segments_mp(R, p2, p3)
+    else:
+        plan, segs = ("single", ref), lib.waveforms.segments_single(R, ref)
+    out = vec.chain(raw, B, P, R, C, plan, k["cfar"], zero_div=k["zdiv"], stc=stc, mti_lag=k["mti"], near_tol=RTOL)
     with lib.Context(0, n_prt=P, n_range=R, n_lanes=C, max_cpi=B, mti_lag=k["mti"], zero_v_div=k["zdiv"], chunk_cpi=k["chunk"],
                      max_det=1 << 21) as ctx:
-        ctx.set_waveform(lib.waveforms.segments_single(R, ref))
+        ctx.set_waveform(segs)
         ctx.set_cfar(*k["cfar"])
         if stc is not None:
             ctx.set_stc(stc)
