@@ -159,7 +159,7 @@ struct rb200_ctx {
     int n_sms = 148;
     // persistent-grid sizing (CTAs per SM): 3/3 fills the SM with one kernel at a time; 2/1 lets the compute-bound PC
     // kernel of chunk i+1 and the HBM-bound MTD kernel of chunk i be co-resident (registers: 2*20.5K + 19.6K <= 64K)
-    int pc_ctas_per_sm = 3, mtd_ctas_per_sm = 3;
+    int pc_ctas_per_sm = 4, mtd_ctas_per_sm = 3;
     // chunk pipelining of the fused path: chunk i runs on slot i % n_slots (own stream + scratch), so the
     // tail of one chunk's kernels overlaps the head of the next while the PC intermediate stays L2-sized
     struct Slot {

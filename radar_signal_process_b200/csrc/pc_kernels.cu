@@ -151,12 +151,17 @@ pc_fft_kernel(const PcParams p) {
 // ---------------------------------------------------------------------------------------------
 // Persistent variant for the wire format with 16 interleaved channels: the raw tile of a work item
 // (NT range cells x 16 channels x 4 B, contiguous in HBM) is fetched by one TMA bulk copy
-// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) into a double-buffered staging area while
-// the CTA is still transforming the previous item, so the global-load latency never stalls the
-// butterflies.  Grid = resident CTAs (SMs x 3); items (line group, tile) are taken round-robin.
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) into a staging buffer.  A tile is consumed
+// into registers at the very top of its item, so the SAME buffer is refilled for the next item as soon as
+// every thread has arrived on the `empty` barrier -- the copy then has the whole transform of the current
+// item to land, and one 16 KB buffer is enough.  With 53 KB of shared memory and 64 registers per thread
+// four CTAs (32 warps) are resident per SM.  Grid = resident CTAs; items (line group, tile) round-robin.
 // ---------------------------------------------------------------------------------------------
+#ifndef RB_PC_TMA_MINB
+#define RB_PC_TMA_MINB 4
+#endif
 template <int R, int S, bool GAIN>
-__global__ void __launch_bounds__(16 * (ipow(R, S) / R), PcOcc<R, S, 16>::min_blocks)
+__global__ void __launch_bounds__(16 * (ipow(R, S) / R), RB_PC_TMA_MINB)
 pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
     constexpr int LT = 16;
     constexpr int NT = ipow(R, S);
@@ -169,9 +174,9 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
     int* rawbuf = reinterpret_cast<int*>(smem_raw + FFT_BYTES);
     // resident tables: stage-major twiddles and up to TAB_SEGS segment spectra (each NT float2)
     constexpr int TW_N = tw_block_off<R, S>(S - 1) > 0 ? tw_block_off<R, S>(S - 1) : 1;
-    float2* tw_sm = reinterpret_cast<float2*>(smem_raw + FFT_BYTES + 2 * RAW_INTS * 4);
+    float2* tw_sm = reinterpret_cast<float2*>(smem_raw + FFT_BYTES + RAW_INTS * 4);
     float2* h_sm = tw_sm + TW_N;
-    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ __align__(8) uint64_t mbar[2];          // [0] full (TMA bytes landed), [1] empty (every thread has read the tile)
     __shared__ float gain_sm[GAIN ? 2 * NT : 1];       // iSTC gains of the current / next tile (blockDim.x == NT threads fill it)
 
     const int t = threadIdx.x;
@@ -179,7 +184,7 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
     const int u = t / LT;
     if (t == 0) {
         mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+        mbar_init(&mbar[1], (int)blockDim.x);
         mbar_fence_init();
     }
     for (int i = t; i < TW_N; i += blockDim.x) tw_sm[i] = __ldg(p.tw + i);
@@ -195,8 +200,8 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
     if (GAIN && (int)blockIdx.x < n_items) stage_gain(blockIdx.x, 0);
     __syncthreads();
 
-    // thread 0: start the bulk copy of an item's valid input span into staging buffer `buf`
-    auto issue = [&](int item, int buf) {
+    // thread 0: start the bulk copy of an item's valid input span into the staging buffer
+    auto issue = [&](int item) {
         const int g = item / n_tiles;
         const int2 tile = __ldg(&p.tiles[item - g * n_tiles]);
         const PcSegDev& sg = p.segs[tile.x];
@@ -205,16 +210,16 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
         const int hi = min(in_off + NT, sg.in_len);
         if (hi > lo) {
             const uint32_t bytes = (uint32_t)(hi - lo) * (LT * 4);
-            mbar_expect_tx(&mbar[buf], bytes);
+            mbar_expect_tx(&mbar[0], bytes);
             const int* src = reinterpret_cast<const int*>(p.in) + ((size_t)g * p.R + sg.in_start + lo) * LT;
-            bulk_g2s(rawbuf + buf * RAW_INTS + (lo - in_off) * LT, src, bytes, &mbar[buf]);
+            bulk_g2s(rawbuf + (lo - in_off) * LT, src, bytes, &mbar[0]);
         } else {
-            mbar_arrive(&mbar[buf]);
+            mbar_arrive(&mbar[0]);
         }
     };
 
     int item = blockIdx.x;
-    if (t == 0 && item < n_items) issue(item, 0);
+    if (t == 0 && item < n_items) issue(item);
     for (int it = 0; item < n_items; item += gridDim.x, ++it) {
         const int buf = it & 1;
         const int g = item / n_tiles;
@@ -222,10 +227,10 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
         const PcSegDev& sg = p.segs[tile.x];
         const int in_off = tile.y * sg.V - sg.pre;
 
-        mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
+        mbar_wait(&mbar[0], (uint32_t)(it & 1));
         float2 v[R];
         {
-            const int* rb = rawbuf + buf * RAW_INTS + u * LT + lane;
+            const int* rb = rawbuf + u * LT + lane;
             const bool interior = in_off >= 0 && in_off + NT <= sg.in_len;
             if (interior) {
 #pragma unroll
@@ -250,13 +255,16 @@ pc_fft_tma_kernel(const PcParams p, int n_items, int n_tiles, int h_entries) {
                 for (int j = 0; j < R; ++j) v[j] = cscale(v[j], gs[GAIN ? j * NB : 0]);
             }
         }
-        // generic-proxy reads of the staging buffer are ordered before the TMA (async-proxy) refill that thread 0
-        // issues for a later item
+        // generic-proxy reads of the staging buffer are ordered before the TMA (async-proxy) refill: every thread fences
+        // and arrives on `empty`; thread 0 refills the buffer for the next item once all arrivals are in
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        // the other staging buffer was consumed one iteration ago (every thread has passed a barrier since)
+        mbar_arrive(&mbar[1]);
         {
             const int next = item + gridDim.x;
-            if (t == 0 && next < n_items) issue(next, buf ^ 1);
+            if (t == 0) {
+                mbar_wait(&mbar[1], (uint32_t)(it & 1));
+                if (next < n_items) issue(next);
+            }
             if (GAIN && next < n_items) stage_gain(next, buf ^ 1);      // read after the end-of-item barrier
         }
         int out_lane, out_u;
@@ -395,20 +403,27 @@ void pc_build_twiddles(int nt, std::vector<float2>& tw) {
 cudaError_t launch_pc_fft_tma(const PcParams& p, int n_tiles, int n_groups, int n_sms, int ctas_per_sm, int h_entries, cudaStream_t st) {
     constexpr int R = 16, S = 2, NT = 256, LT = 16;
     const size_t fft_bytes = ((size_t)LT * (NT + 1) * sizeof(float2) + 127) / 128 * 128;
-    const size_t smem = fft_bytes + 2 * (size_t)NT * LT * 4 + ((size_t)tw_block_off<R, S>(S - 1) + h_entries) * sizeof(float2);
+    const size_t smem = fft_bytes + (size_t)NT * LT * 4 + ((size_t)tw_block_off<R, S>(S - 1) + h_entries) * sizeof(float2);
     const long long n_items = (long long)n_tiles * n_groups;
     if (n_items <= 0 || n_items > 0x7fffffffLL) return n_items <= 0 ? cudaSuccess : cudaErrorInvalidConfiguration;
-    const int per_sm = std::max(1, std::min(ctas_per_sm, (int)PcOcc<R, S, LT>::min_blocks));
-    const int grid = (int)std::min<long long>(n_items, (long long)n_sms * per_sm);
+    // resident CTAs per SM as the hardware will actually place them (shared memory grows with the number of segment spectra)
+    auto resident = [&](auto kernel, size_t (&configured)[64]) -> int {
+        if (ensure_dynamic_smem(kernel, smem, configured) != cudaSuccess) return -1;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, LT * (NT / R), smem) != cudaSuccess) return -1;
+        return std::max(1, std::min(std::min(ctas_per_sm, RB_PC_TMA_MINB), nb));
+    };
     if (p.gain) {
         static size_t configured[64] = {};
-        cudaError_t ce = ensure_dynamic_smem(pc_fft_tma_kernel<R, S, true>, smem, configured);
-        if (ce != cudaSuccess) return ce;
+        const int per_sm = resident(pc_fft_tma_kernel<R, S, true>, configured);
+        if (per_sm < 0) return cudaGetLastError() != cudaSuccess ? cudaErrorInvalidValue : cudaErrorInvalidValue;
+        const int grid = (int)std::min<long long>(n_items, (long long)n_sms * per_sm);
         pc_fft_tma_kernel<R, S, true><<<grid, LT * (NT / R), smem, st>>>(p, (int)n_items, n_tiles, h_entries);
     } else {
         static size_t configured[64] = {};
-        cudaError_t ce = ensure_dynamic_smem(pc_fft_tma_kernel<R, S, false>, smem, configured);
-        if (ce != cudaSuccess) return ce;
+        const int per_sm = resident(pc_fft_tma_kernel<R, S, false>, configured);
+        if (per_sm < 0) return cudaErrorInvalidValue;
+        const int grid = (int)std::min<long long>(n_items, (long long)n_sms * per_sm);
         pc_fft_tma_kernel<R, S, false><<<grid, LT * (NT / R), smem, st>>>(p, (int)n_items, n_tiles, h_entries);
     }
     return cudaGetLastError();
