@@ -33,7 +33,7 @@ P, R, C = 64, 4096, 16
 CELLS = P * R * C
 ALG_BYTES_PER_CPI = CELLS * 8          # 4 B int16 I/Q read + 4 B fp32 RDM magnitude written per cell
 CFAR = (5, 7, 5.0, 0, 5, 7, 5.0, 0, 0, 1)
-K1_DRAM_BYTES_PER_CPI = (134.603008e6 + 212.313344e6) / 8.0     # ncu, cold cache, see profiles/r01d_ncu_full_chunk8.txt
+K1_DRAM_BYTES_PER_CPI = (134.590208e6 + 215.659008e6) / 8.0     # ncu, cold cache, see profiles/r01j_ncu_full_final.txt
 METRIC = "CPI frames/s (PC->MTD->0v->CFAR, 64 PRT x 4096 range x 16 lanes int16 DDC)"
 
 
@@ -375,8 +375,8 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "kernel": "pc_fft_tma_kernel (K1: int16 unpack + overlap-save pulse compression; 60 % of the chain's device time)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the ncu --set full
-                         # capture profiles/r01d_ncu_full_chunk8.txt (134.6 MB read + 212.3 MB written per 8-CPI launch)
-                         "traffic": K1_DRAM_BYTES_PER_CPI * cpis_per_launch, "traffic_source": "profiles/r01d_ncu_full_chunk8.txt",
+                         # capture profiles/r01j_ncu_full_final.txt (134.6 MB read + 215.7 MB written per 8-CPI launch)
+                         "traffic": K1_DRAM_BYTES_PER_CPI * cpis_per_launch, "traffic_source": "profiles/r01j_ncu_full_final.txt",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_CPI * cpis_per_launch,
                          "ms_per_launch": pc_ms_per_launch,
