@@ -235,6 +235,11 @@ int rb200_reader_state(const rb200_reader* r, int* file_index, long long* pos);
 int rb200_reader_next_frame_ddc(rb200_reader* r, int n_prt, int n_range, int n_channels, int16_t* raw_out,
                                 uint32_t* frame_no, uint16_t* servo_angle, uint64_t* timer_cnt,
                                 int* prts_read, int* end_of_stream);
+/* Same for DBF-type frames (data_type 2, FrameDataRead_xzr.m:111-119): payload_out receives n_prt padded PRT payloads
+ * (n_range * (6*n_channels + pad) bytes, rounded up to 64) back to back -- the input layout of rb200_chain_dbf24.   */
+int rb200_reader_next_frame_dbf24(rb200_reader* reader, int n_prt, int n_range, int n_channels, uint8_t* payload_out,
+                                  uint32_t* frame_no, uint16_t* servo_angle, uint64_t* timer_cnt,
+                                  int* prts_read, int* end_of_stream);
 
 /* f3: [rEst, vEst, eleEst] = motionParaMeasure(sum, diff, flags, extraDots, rScale, deltaR, rInterpTimes, vScale, deltaV,
  *          vInterpTimes, kValues, beamPosNum, beamAngleStep, freInd, eleAngleComp, eleAngleSysErr, MTD_0_num)

@@ -173,3 +173,16 @@ def to_dbf24(lanes, channel_num):
             rows[:, :, o + 1] = (w >> 8) & 0xFF
             rows[:, :, o + 2] = (w >> 16) & 0xFF
     return out
+
+
+def frame_prt_dbf24(payload_bytes, n_range, frame_no=0, prt_no=0, channel_num=13, servo=0):
+    """Wrap one DBF-type PRT payload (already padded, see to_dbf24) in the 64 B head / 128 B realtime / 64 B tail framing
+    with data_type = 2 (FrameDataRead_xzr.m:62-119,184)."""
+    head = np.zeros(16, dtype="<u4")
+    head[0] = frame_no
+    head[2] = prt_no & 0xFFFF
+    head[3] = channel_num & 0xFF
+    head[4] = servo & 0xFFFF
+    head[6] = n_range
+    head[7] = 2
+    return head.tobytes() + bytes(128) + bytes(np.ascontiguousarray(payload_bytes, dtype=np.uint8)) + bytes(64)

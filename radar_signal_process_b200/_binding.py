@@ -63,7 +63,7 @@ EXPORTS = [
     "rb200_cfar1d_fix_d", "rb200_execute_cfar_d", "rb200_unpack_ddc_i16", "rb200_chain_i16",
     "rb200_chain_enqueue", "rb200_chain_fetch", "rb200_debug_fetch_pc", "rb200_last_device_ms",
     "rb200_last_launch_count", "rb200_set_dbf", "rb200_set_stage_timing", "rb200_get_stage_ms", "rb200_unpack_dbf24", "rb200_chain_dbf24", "rb200_mtd_produce_windows_z", "rb200_dmx_process_z", "rb200_motion_para_measure_d", "rb200_reader_open", "rb200_reader_close",
-    "rb200_reader_last_error", "rb200_reader_state", "rb200_reader_next_frame_ddc",
+    "rb200_reader_last_error", "rb200_reader_state", "rb200_reader_next_frame_ddc", "rb200_reader_next_frame_dbf24",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def load():
     lib.rb200_reader_last_error.restype = C.c_char_p
     lib.rb200_reader_state.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
     lib.rb200_reader_next_frame_ddc.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.rb200_reader_next_frame_dbf24.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

@@ -131,12 +131,13 @@ extern "C" int rb200_reader_state(const rb200_reader* r, int* file_index, long l
     return RB200_OK;
 }
 
-// One logical frame of n_prt DDC PRTs (FrameDataRead_xzr.m:57-198, data_type 1).  raw_out receives
-// [prt][range][channel][I,Q] int16.  Per-PRT header fields go to the optional arrays.
-extern "C" int rb200_reader_next_frame_ddc(rb200_reader* r, int n_prt, int n_range, int n_channels, int16_t* raw_out,
-                                           uint32_t* frame_no, uint16_t* servo_angle, uint64_t* timer_cnt,
-                                           int* prts_read, int* end_of_stream) {
-    if (!r || !raw_out || n_prt < 1 || n_range < 1 || n_channels < 1 || !prts_read || !end_of_stream) return RB200_ERR_ARG;
+// One logical frame of n_prt PRTs of the wanted data type (FrameDataRead_xzr.m:57-198).  DDC (data_type 1): out receives
+// the payload only, [prt][range][channel][I,Q] int16.  DBF-type (data_type 2): out receives every PRT's payload including
+// its padding to 64 bytes, exactly the layout rb200_chain_dbf24 / rb200_unpack_dbf24 take.  Per-PRT header fields go to the
+// optional arrays.
+static int next_frame(rb200_reader* r, int want_type, int n_prt, int n_range, int n_channels, uint8_t* out, uint32_t* frame_no,
+                      uint16_t* servo_angle, uint64_t* timer_cnt, int* prts_read, int* end_of_stream) {
+    if (!r || !out || n_prt < 1 || n_range < 1 || n_channels < 1 || !prts_read || !end_of_stream) return RB200_ERR_ARG;
     *prts_read = 0;
     *end_of_stream = 0;
     const long long head_b = 64, rt_b = 128, tail_b = 64;             // bin_to_mat_xzr.m:41-43
@@ -160,14 +161,19 @@ extern "C" int rb200_reader_next_frame_ddc(rb200_reader* r, int n_prt, int n_ran
         const long long padded = sig + ((sig % 64) ? 64 - sig % 64 : 0);                                         // :115-119
         buf.resize((size_t)padded);
         if (stream_read(r, buf.data(), padded, &eos) < padded || eos) { *end_of_stream = 1; return RB200_OK; }   // :122-127
-        if (data_type != 1) { r->err = "rb200_reader_next_frame_ddc: PRT is not DDC data (data_type != 1)"; return RB200_ERR_UNSUPPORTED; }
+        if ((int)data_type != want_type) {
+            r->err = want_type == 1 ? "rb200_reader_next_frame_ddc: PRT is not DDC data (data_type != 1)"
+                                    : "rb200_reader_next_frame_dbf24: PRT is not DBF-type data (data_type != 2)";
+            return RB200_ERR_UNSUPPORTED;
+        }
         // :171-176 size check of the parsed PRT against the configured geometry
         if ((int)pulse_data_num != n_range || (int)channel_num != n_channels) {
             *end_of_stream = 1;
             r->err = "PRT geometry differs from the configured point_PRT / channel_num";
             return RB200_OK;
         }
-        memcpy(raw_out + (size_t)prt * n_range * n_channels * 2, buf.data(), (size_t)n_range * n_channels * 4);   // :138,150 (payload only)
+        if (want_type == 1) memcpy(out + (size_t)prt * n_range * n_channels * 4, buf.data(), (size_t)n_range * n_channels * 4);   // :138,150
+        else memcpy(out + (size_t)prt * (size_t)padded, buf.data(), (size_t)padded);                               // :130-135 decode on the device
         if (frame_no) frame_no[prt] = h[0];                           // :74
         if (servo_angle) servo_angle[prt] = (uint16_t)(h[4] & 0xFFFFu);   // :78
         if (timer_cnt) timer_cnt[prt] = (uint64_t)h[8] + ((uint64_t)h[9] << 32);   // :83
@@ -176,4 +182,17 @@ extern "C" int rb200_reader_next_frame_ddc(rb200_reader* r, int n_prt, int n_ran
         if (stream_read(r, tail, tail_b, &eos) < tail_b || eos) { *end_of_stream = 1; return RB200_OK; }          // :184-189
     }
     return RB200_OK;
+}
+
+extern "C" int rb200_reader_next_frame_ddc(rb200_reader* r, int n_prt, int n_range, int n_channels, int16_t* raw_out,
+                                           uint32_t* frame_no, uint16_t* servo_angle, uint64_t* timer_cnt,
+                                           int* prts_read, int* end_of_stream) {
+    return next_frame(r, 1, n_prt, n_range, n_channels, reinterpret_cast<uint8_t*>(raw_out), frame_no, servo_angle, timer_cnt, prts_read,
+                      end_of_stream);
+}
+
+extern "C" int rb200_reader_next_frame_dbf24(rb200_reader* r, int n_prt, int n_range, int n_channels, uint8_t* payload_out,
+                                             uint32_t* frame_no, uint16_t* servo_angle, uint64_t* timer_cnt,
+                                             int* prts_read, int* end_of_stream) {
+    return next_frame(r, 2, n_prt, n_range, n_channels, payload_out, frame_no, servo_angle, timer_cnt, prts_read, end_of_stream);
 }

@@ -717,3 +717,38 @@ def test_chain_S5_full_size_two_lanes_against_oracle(lib):
         d = dets[dets["lane"] == lane].copy()
         d["lane"] = 0
         _compare_flags(d, out, 1, 1, P, R, lib)
+
+
+def test_dbf24_capture_files_to_detections_end_to_end(lib, tmp_path):
+    """f2 + f1 + the hot path on DBF-type captures: framed files (data_type 2) -> C++ reader -> rb200_chain_dbf24 -> detections,
+    against the oracle's 24-bit decoder + chain on the same bytes."""
+    from radar_signal_process_b200.reader import FrameReader
+    P, R, n_ch, B = 64, 300, 13, 2
+    ref = mcode.load_ref("refDBFDataMF1")
+    rng = np.random.default_rng(21)
+    sig, pad, osp = mcode.dbf24_payload_size(R, n_ch)
+    ncol = ((n_ch * 6 + osp) // 3) // 2
+    lanes = np.round(rng.normal(0, 2000, (B, P, R, ncol))) + 1j * np.round(rng.normal(0, 2000, (B, P, R, ncol)))
+    for b in range(B):
+        echo = (25000.0 / np.abs(ref).max()) * ref[None, :] * np.exp(2j * np.pi * (0.13 + 0.2 * b) * np.arange(P))[:, None]
+        lanes[b, :, 90:90 + ref.size, 3 + b] += np.round(echo.real) + 1j * np.round(echo.imag)
+    blob = b"".join(synth.frame_prt_dbf24(synth.to_dbf24(lanes[b, p:p + 1], n_ch)[0], R, frame_no=b, prt_no=p, channel_num=n_ch)
+                    for b in range(B) for p in range(P))
+    cut = len(blob) // 2 + 33
+    (tmp_path / "1.000001.bin").write_bytes(blob[:cut])
+    (tmp_path / "1.000002.bin").write_bytes(blob[cut:])
+    rd = FrameReader(tmp_path)
+    frames = []
+    for b in range(B):
+        payload, meta, nread, eos = rd.next_frame_dbf24(P, R, n_ch)
+        assert nread == P and not eos and np.all(meta["frame_no"] == b)
+        frames.append(payload.copy())
+    batch = np.stack(frames)                                                     # [cpi][prt][padded bytes]
+    cfar = (5, 7, 6.0, 0, 5, 7, 6.0, 0, 0, 1)
+    out = vec.chain_lanes(lanes.transpose(0, 3, 1, 2), ("single", ref), cfar, near_tol=RTOL)
+    with _chain_ctx(lib, P, R, ncol, B, lib.waveforms.segments_single(R, ref), cfar, max_det=1 << 20) as ctx:
+        rdm, dets, n = ctx.chain_dbf24(batch, n_ch, B)
+    _close(rdm, out["rdm"])
+    _compare_flags(dets, out, B, ncol, P, R, lib)
+    flag, _ = lib.dets_to_flags(dets, B, ncol, P, R)
+    assert flag[0, 3].sum() > 0 and flag[1, 4].sum() > 0

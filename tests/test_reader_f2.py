@@ -93,3 +93,28 @@ def test_reader_truncated_stream_and_geometry_mismatch(tmp_path):
     assert nread == 0 and eos
     with pytest.raises(Exception):
         FrameReader(tmp_path / "does_not_exist")
+
+
+def test_reader_dbf24_frames_round_trip_and_type_check(tmp_path):
+    """DBF-type captures (data_type 2): the reader hands back the padded 24-bit payloads the device decoder takes; asking for
+    DDC frames on such a capture is refused."""
+    n_frames, n_prt, n_range, ch = 2, 3, 29, 13
+    rng = np.random.default_rng(5)
+    sig, pad, osp = mcode.dbf24_payload_size(n_range, ch)
+    ncol = ((ch * 6 + osp) // 3) // 2
+    lanes = rng.integers(-(1 << 23) + 1, 1 << 23, size=(n_frames, n_prt, n_range, ncol)) + 1j * rng.integers(-(1 << 23) + 1, 1 << 23, size=(n_frames, n_prt, n_range, ncol))
+    payloads = np.stack([synth.to_dbf24(lanes[f], ch) for f in range(n_frames)])                 # [frame][prt][bytes]
+    blob = b"".join(synth.frame_prt_dbf24(payloads[f, p], n_range, frame_no=f, prt_no=p, channel_num=ch, servo=11 * p)
+                    for f in range(n_frames) for p in range(n_prt))
+    _write_capture(tmp_path, blob, [len(blob) // 3 + 7])
+    rd = FrameReader(tmp_path)
+    for f in range(n_frames):
+        got, meta, nread, eos = rd.next_frame_dbf24(n_prt, n_range, ch)
+        assert nread == n_prt and not eos
+        assert np.array_equal(got, payloads[f])
+        assert np.array_equal(meta["frame_no"], np.full(n_prt, f)) and np.array_equal(meta["servo_angle"], 11 * np.arange(n_prt))
+        for p in range(n_prt):                                                                    # and they decode to the lanes
+            assert np.array_equal(mcode.unpack_dbf24(got[p], n_range, ch), lanes[f, p])
+    assert rd.next_frame_dbf24(n_prt, n_range, ch)[2:] == (0, True)
+    with pytest.raises(Exception):
+        FrameReader(tmp_path).next_frame(n_prt, n_range, ch)
