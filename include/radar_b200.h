@@ -118,7 +118,14 @@ int rb200_create(rb200_ctx** out, int device, const rb200_config* cfg);
 int rb200_destroy(rb200_ctx* ctx);
 const char* rb200_last_error(const rb200_ctx* ctx);           /* NULL ctx -> last create() error    */
 int rb200_get_config(const rb200_ctx* ctx, rb200_config* out);
-int rb200_set_cfar(rb200_ctx* ctx, const rb200_config* cfg);  /* update only the cfar_* fields      */
+int rb200_set_cfar(rb200_ctx* ctx, const rb200_config* cfg);
+
+/* Range segments of the chain's CFAR = the local function fun_CFARflag of CW/main_cfar.m:142-161 (columns 1:82, 83:318,
+ * 319:868 there): executeCFAR runs on every segment separately, so range windows never straddle a waveform segment, and
+ * columns outside every segment are left 0.  lo/hi: 0-based half-open column ranges, ascending and disjoint, n <= 4;
+ * n = 0 restores one segment covering the whole PRT.  A segment too short for the range windows raises
+ * RB200_ERR_INDEX at the next chain call, as Function_CFAR1D_sub_fixCells.m:39-58 would.                             */
+int rb200_set_cfar_segments(rb200_ctx* ctx, const int32_t* lo, const int32_t* hi, int n);  /* update only the cfar_* fields      */
 
 /* Precompute and keep resident the reference spectra of every segment.  Replaces the per-PRT
  * fft(h,n) of MP/fun_pulse_compression.m:20.                                                      */

@@ -62,7 +62,7 @@ EXPORTS = [
     "rb200_process_mtd_z", "rb200_zero_v_pressing_d", "rb200_mtd_produce_z", "rb200_cfar1d_sub_d",
     "rb200_cfar1d_fix_d", "rb200_execute_cfar_d", "rb200_unpack_ddc_i16", "rb200_chain_i16",
     "rb200_chain_enqueue", "rb200_chain_fetch", "rb200_debug_fetch_pc", "rb200_last_device_ms",
-    "rb200_last_launch_count", "rb200_set_dbf", "rb200_set_stage_timing", "rb200_get_stage_ms", "rb200_unpack_dbf24", "rb200_chain_dbf24", "rb200_mtd_produce_windows_z", "rb200_dmx_process_z", "rb200_motion_para_measure_d", "rb200_reader_open", "rb200_reader_close",
+    "rb200_last_launch_count", "rb200_set_dbf", "rb200_set_cfar_segments", "rb200_set_stage_timing", "rb200_get_stage_ms", "rb200_unpack_dbf24", "rb200_chain_dbf24", "rb200_mtd_produce_windows_z", "rb200_dmx_process_z", "rb200_motion_para_measure_d", "rb200_reader_open", "rb200_reader_close",
     "rb200_reader_last_error", "rb200_reader_state", "rb200_reader_next_frame_ddc", "rb200_reader_next_frame_dbf24",
 ]
 
@@ -109,6 +109,7 @@ def load():
     lib.rb200_set_stage_timing.argtypes = [vp, C.c_int]
     lib.rb200_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rb200_unpack_dbf24.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_int)]
+    lib.rb200_set_cfar_segments.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
     lib.rb200_chain_dbf24.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int), vp]
     lib.rb200_mtd_produce_windows_z.argtypes = [vp, dp, dp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_double, C.c_int, dp]
     lib.rb200_dmx_process_z.argtypes = [vp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_int, dp, dp, C.c_int, C.c_int, dp, C.c_int, C.c_int,

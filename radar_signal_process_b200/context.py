@@ -148,6 +148,12 @@ class Context:
             out[i] = buf[i * win_len * R:(i + 1) * win_len * R].reshape((int(win_len), R), order="F")
         return out
 
+    def set_cfar_segments(self, segments):
+        """fun_CFARflag (CW/main_cfar.m:142-161): 0-based half-open (lo, hi) column ranges; [] = whole PRT."""
+        lo = np.ascontiguousarray([s[0] for s in segments], dtype=np.int32)
+        hi = np.ascontiguousarray([s[1] for s in segments], dtype=np.int32)
+        self._ck(self._lib.rb200_set_cfar_segments(self._h, lo.ctypes.data_as(C.POINTER(C.c_int32)), hi.ctypes.data_as(C.POINTER(C.c_int32)), len(segments)))
+
     def dmx_process(self, left, right, n_short, fir_taps, mf_taps, fft_num, mtd_window, mtd_fft_num, n_blank):
         """One frame of the DMX script variant (CW/DMX_SignalProcessing_main_xzr.m:332-426,462-465).
 

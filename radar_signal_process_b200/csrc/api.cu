@@ -145,6 +145,7 @@ struct rb200_ctx {
     rb200_config cfg;
     std::string err;
     Plan plan;
+    CfarSegs cfar_segs = {};       // rb200_set_cfar_segments (fun_CFARflag); n = 0: whole range axis
     Plan dmx_plan;                 // private plan of rb200_dmx_process_z (never touches the caller's waveform)
     unsigned long long dmx_key = 0;
     std::map<std::pair<int, long long>, MtdPlan*> mtd_plans;
@@ -701,6 +702,19 @@ extern "C" int rb200_set_stc(rb200_ctx* c, const double* stc_db, int n) {
     CK(c, cudaMemcpyAsync(c->gain.p, g.data(), R * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     c->gain_n = n;
+    return RB200_OK;
+}
+
+extern "C" int rb200_set_cfar_segments(rb200_ctx* c, const int32_t* lo, const int32_t* hi, int n) {
+    if (!c || n < 0 || n > 4 || (n > 0 && (!lo || !hi))) return fail(c, RB200_ERR_ARG, "set_cfar_segments: 0..4 segments");
+    CfarSegs s = {};
+    for (int i = 0; i < n; ++i) {
+        if (lo[i] < 0 || hi[i] <= lo[i] || (i > 0 && lo[i] < hi[i - 1])) return fail(c, RB200_ERR_ARG, "set_cfar_segments: segments must be ascending, non-empty and disjoint");
+        s.lo[i] = lo[i];
+        s.hi[i] = hi[i];
+    }
+    s.n = n;
+    c->cfar_segs = s;
     return RB200_OK;
 }
 
@@ -1310,6 +1324,9 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     cp.range_stage = k.cfar_range_stage ? 1 : 0;
     cp.max_det = k.max_det;
     cp.n_lanes = C;
+    cp.segs = c->cfar_segs;
+    for (int i = 0; i < cp.segs.n; ++i)
+        if (cp.segs.hi[i] > R) return fail(c, RB200_ERR_INDEX, "fun_CFARflag: Index in position 2 exceeds array bounds (range segment past the PRT length)");
     c->launches = 0;
     CK(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(int), st));
     CK(c, cudaMemsetAsync(c->errflag.p, 0, sizeof(int), st));
@@ -1363,6 +1380,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
             q.m.cols_ld = R;
             q.m.max_det = k.max_det;
             q.m.n_lanes = C;
+            q.m.segs = c->cfar_segs;
             q.m.cpi0 = 0;
             q.n_cpi = n_cpi;
             q.n_tiles = c->plan.classes[0].n_tiles;
@@ -1411,6 +1429,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         m64.cols_ld = R;
         m64.max_det = k.max_det;
         m64.n_lanes = C;
+        m64.segs = c->cfar_segs;
         const char* env = getenv("RB200_SLOTS");
         n_slots = env ? atoi(env) : 3;
         n_slots = std::max(1, std::min(n_slots, (int)rb200_ctx::kMaxSlots));

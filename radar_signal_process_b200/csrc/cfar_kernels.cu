@@ -40,7 +40,8 @@ __global__ void cfar_v_kernel(const T* __restrict__ rdm, const CfarParams p, T t
     const int r = blockIdx.x * blockDim.x + threadIdx.x;      // blockDim.x is a multiple of 32
     const int lane = threadIdx.x & 31;
     const int word = r >> 5;
-    const bool in_range = r < p.R;
+    int slo_, shi_;
+    const bool in_range = r < p.R && cfar_seg_of(p.segs, r, p.R, &slo_, &shi_);     // columns outside every segment: no hits
     const T* slab_base = rdm + (size_t)slab * p.V * p.R;
     const T* col = ROWMAJOR ? slab_base + (size_t)p.v_lo * p.R + (in_range ? r : 0) : slab_base + p.v_lo + (size_t)p.V * (in_range ? r : 0);
     const ptrdiff_t sv = ROWMAJOR ? p.R : 1;
@@ -93,7 +94,8 @@ cfar_v_tiled_kernel(const float* __restrict__ rdm, const CfarParams p, float t_v
     const int r = blockIdx.x * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int word = r >> 5;
-    const bool in_range = r < p.R;
+    int slo_, shi_;
+    const bool in_range = r < p.R && cfar_seg_of(p.segs, r, p.R, &slo_, &shi_);
     const float* col = rdm + ((size_t)slab * p.V + p.v_lo) * p.R + (in_range ? r : 0);
     const int y_begin = blockIdx.z * rows_per_seg;
     const int y_end = min(nv, y_begin + rows_per_seg);
@@ -138,15 +140,16 @@ cfar_v_tiled_kernel(const float* __restrict__ rdm, const CfarParams p, float t_v
 }
 
 template <typename T, bool ROWMAJOR>
-__device__ __forceinline__ int cfar_elect(const T* __restrict__ row, ptrdiff_t sr, int r, const CfarParams& p, T t_r, int* err_flag) {
-    // first maximum among the passing cells of {r-1, r, r+1} (executeCFAR.m:50-73); -1 if none
+__device__ __forceinline__ int cfar_elect(const T* __restrict__ row, ptrdiff_t sr, int r, int N, const CfarParams& p, T t_r, int* err_flag) {
+    // first maximum among the passing cells of {r-1, r, r+1} (executeCFAR.m:50-73); -1 if none.  row points at the first
+    // cell of the range segment, r is relative to it, N is the segment length.
     int best = -1;
     T bestv = 0;
 #pragma unroll
     for (int d = -1; d <= 1; ++d) {
         const int c = r + d;
-        if (c < 0 || c >= p.R) continue;
-        if (!cfar_decide<T>(row, sr, c, p.R, p.ref_r, p.guard_r, t_r, p.meth_r, err_flag)) continue;
+        if (c < 0 || c >= N) continue;
+        if (!cfar_decide<T>(row, sr, c, N, p.ref_r, p.guard_r, t_r, p.meth_r, err_flag)) continue;
         const T x = row[(ptrdiff_t)c * sr];
         if (best < 0 || x > bestv) { best = c; bestv = x; }
     }
@@ -170,8 +173,13 @@ __global__ void cfar_r_kernel(const T* __restrict__ rdm, const CfarParams p, T t
     const T* slab_base = rdm + (size_t)slab * p.V * p.R;
     const T* row = ROWMAJOR ? slab_base + (size_t)v * p.R : slab_base + v;
     const ptrdiff_t sr = ROWMAJOR ? 1 : p.V;
-    const int c = cfar_elect<T, ROWMAJOR>(row, sr, r, p, t_r, err_flag);
-    if (c < 0) return;
+    int slo, shi;
+    if (!cfar_seg_of(p.segs, r, p.R, &slo, &shi)) return;
+    const T* srow = row + (ptrdiff_t)slo * sr;
+    const int N = shi - slo;
+    const int crel = cfar_elect<T, ROWMAJOR>(srow, sr, r - slo, N, p, t_r, err_flag);
+    if (crel < 0) return;
+    const int c = crel + slo;
     if (flag2d) {
         flag2d[ROWMAJOR ? ((size_t)slab * p.V + v) * p.R + c : (size_t)slab * p.V * p.R + v + (size_t)p.V * c] = 1;
         if (!dets_2d) return;
@@ -180,9 +188,9 @@ __global__ void cfar_r_kernel(const T* __restrict__ rdm, const CfarParams p, T t
     const int Rw = (p.R + 31) / 32;
     const uint32_t* mrow = vmask + ((size_t)slab * p.V + v) * Rw;
     for (int rr = c - 1; rr < r; ++rr) {
-        if (rr < 0) continue;
+        if (rr < slo) continue;
         if (!((mrow[rr >> 5] >> (rr & 31)) & 1u)) continue;
-        if (cfar_elect<T, ROWMAJOR>(row, sr, rr, p, t_r, nullptr) == c) return;
+        if (cfar_elect<T, ROWMAJOR>(srow, sr, rr - slo, N, p, t_r, nullptr) == crel) return;
     }
     const int slot = atomicAdd(count_2d, 1);
     if (slot < p.max_det) {

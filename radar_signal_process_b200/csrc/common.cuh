@@ -49,6 +49,19 @@ struct PcParams {
     int n_lines;            // planar: number of lines
 };
 
+// Range segments of the CFAR (fun_CFARflag, CW/main_cfar.m:142-161): the range stage never looks across a segment border
+// and columns outside every segment produce no detections.  n = 0: one segment covering the whole axis.
+struct CfarSegs {
+    int n;
+    int lo[4], hi[4];       // 0-based [lo, hi)
+};
+__host__ __device__ __forceinline__ bool cfar_seg_of(const CfarSegs& s, int r, int R, int* lo, int* hi) {
+    if (s.n == 0) { *lo = 0; *hi = R; return r >= 0 && r < R; }
+    for (int i = 0; i < s.n; ++i)
+        if (r >= s.lo[i] && r < s.hi[i]) { *lo = s.lo[i]; *hi = s.hi[i]; return true; }
+    return false;
+}
+
 struct CfarParams {
     int V, R;               // full RDM size
     int v_lo, v_hi;         // 0-based tested rows [v_lo, v_hi)  (n0+1 .. V-n0)
@@ -58,6 +71,7 @@ struct CfarParams {
     int max_det;
     int n_lanes;            // slabs per CPI (detection record: cpi = slab / n_lanes, lane = slab % n_lanes)
     int cpi0;               // CPI index of slab 0 (chunked batches)
+    CfarSegs segs;
 };
 
 struct MtdParams {
@@ -102,6 +116,7 @@ struct Mtd64Params {
     unsigned long long* colmask;   // [slab][cols_ld]: bit v set = velocity hit at (v, r)
     int cols_ld;
     int max_det, n_lanes, cpi0;
+    CfarSegs segs;          // velocity hits in columns outside every segment are dropped
 };
 
 // fused persistent chain for P = 64, 16 channels (chain64_kernel.cu)

@@ -77,7 +77,10 @@ __device__ __forceinline__ void mtd64_column(float2 (&v)[64], const Mtd64Params&
         const float mu = p.meth_v == 0 ? fmaxf(a, b) : fminf(a, b);
         if (mag[N0 + 1 + y] >= mu * p.tv_over_ref) hits |= 1ull << (N0 + 1 + y);
     }
-    if (!ok) hits = 0ull;
+    {
+        int slo, shi;
+        if (!ok || !cfar_seg_of(p.segs, r, p.cols, &slo, &shi)) hits = 0ull;
+    }
     if (ok) p.colmask[(size_t)slab * p.cols_ld + r] = hits;
     // ---- compaction: one atomic per warp ----
     if (!__any_sync(0xffffffffu, hits != 0ull)) return;

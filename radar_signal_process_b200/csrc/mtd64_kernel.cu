@@ -167,16 +167,17 @@ __device__ __forceinline__ bool cfar_decide_f32(const float* __restrict__ row, i
     return x >= mu * thr;
 }
 
+// row points at the first cell of the range segment, r is relative to it, N is the segment length
 template <int REF>
-__device__ __forceinline__ int cfar_elect_f32(const float* __restrict__ row, int r, const CfarParams& p, float t_r, int* err_flag) {
+__device__ __forceinline__ int cfar_elect_f32(const float* __restrict__ row, int r, int N, const CfarParams& p, float t_r, int* err_flag) {
     // the three decisions are evaluated unconditionally first (their loads overlap), then combined in column order
     bool pass[3];
     float x[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         const int c = r + d - 1;
-        const bool inside = c >= 0 && c < p.R;
-        pass[d] = inside && cfar_decide_f32<REF>(row, inside ? c : r, p.R, p.ref_r, p.guard_r, t_r, p.meth_r, err_flag);
+        const bool inside = c >= 0 && c < N;
+        pass[d] = inside && cfar_decide_f32<REF>(row, inside ? c : r, N, p.ref_r, p.guard_r, t_r, p.meth_r, err_flag);
         x[d] = inside ? __ldg(row + c) : 0.f;
     }
     int best = -1;
@@ -221,15 +222,19 @@ __global__ void cfar_r64_kernel(const float* __restrict__ rdm, const CfarParams 
         if (!p.range_stage) continue;
         const int slab = (int)(h.cpi - p.cpi0) * p.n_lanes + h.lane;
         const int v = h.v, r = (int)h.r;
-        const float* row = rdm + ((size_t)slab * p.V + v) * p.R;
-        const int c = cfar_elect_f32<REF>(row, r, p, t_r, err_flag);
-        if (c < 0) continue;
+        int slo, shi;
+        if (!cfar_seg_of(p.segs, r, p.R, &slo, &shi)) continue;          // cannot happen: K2 drops such hits
+        const float* row = rdm + ((size_t)slab * p.V + v) * p.R + slo;       // the hit's range segment
+        const int N = shi - slo;
+        const int crel = cfar_elect_f32<REF>(row, r - slo, N, p, t_r, err_flag);
+        if (crel < 0) continue;
+        const int c = crel + slo;
         const unsigned long long* cm = colmask + (size_t)slab * cols_ld;
         bool owner = true;
         for (int rr = c - 1; rr < r && owner; ++rr) {
-            if (rr < 0) continue;
+            if (rr < slo) continue;
             if (!((cm[rr] >> v) & 1ull)) continue;
-            if (cfar_elect_f32<REF>(row, rr, p, t_r, nullptr) == c) owner = false;
+            if (cfar_elect_f32<REF>(row, rr - slo, N, p, t_r, nullptr) == crel) owner = false;
         }
         if (!owner) continue;
         const int slot = warp_agg_slot(&gcount[1]);
@@ -240,7 +245,7 @@ __global__ void cfar_r64_kernel(const float* __restrict__ rdm, const CfarParams 
             d.v = h.v;
             d.lane = h.lane;
             d.kind = RB200_DET_2D;
-            d.amp = row[c];
+            d.amp = row[crel];
             dets_2d[slot] = d;
         }
     }

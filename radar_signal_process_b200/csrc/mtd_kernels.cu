@@ -183,7 +183,10 @@ mtd_fast_kernel(const MtdParams p) {
             hits |= (xc[i] >= mu * p.t_v ? 1u : 0u) << i;
         }
     }
-    if (!ok) hits = 0u;
+    {
+        int slo, shi;
+        if (!ok || !cfar_seg_of(p.cf.segs, r, p.cf.R, &slo, &shi)) hits = 0u;      // columns outside every range segment
+    }
     const int Rw = (p.cf.R + 31) / 32;
     const int lane = threadIdx.x & 31;
     uint32_t* vm = p.vmask + ((size_t)slab * p.cf.V + u * R) * Rw + (r >> 5);   // a warp covers 32 consecutive columns

@@ -752,3 +752,48 @@ def test_dbf24_capture_files_to_detections_end_to_end(lib, tmp_path):
     _compare_flags(dets, out, B, ncol, P, R, lib)
     flag, _ = lib.dets_to_flags(dets, B, ncol, P, R)
     assert flag[0, 3].sum() > 0 and flag[1, 4].sum() > 0
+
+
+def _segmented_cfar_oracle(rdm, cfar, segments):
+    """fun_CFARflag (CW/main_cfar.m:142-161) with the dense oracle: executeCFAR per range segment, zeros elsewhere."""
+    out = {k: np.zeros(rdm.shape, dtype=bool) for k in ("flag", "flagV", "near", "nearV")}
+    for lo, hi in segments:
+        f, fv, near, nearv = vec.execute_cfar(rdm[..., lo:hi], *cfar, near_tol=RTOL)
+        out["flag"][..., lo:hi], out["flagV"][..., lo:hi] = f.astype(bool), fv.astype(bool)
+        out["near"][..., lo:hi], out["nearV"][..., lo:hi] = near, nearv
+    return out
+
+
+@pytest.mark.parametrize("P,C,B,mti", [(64, 16, 2, 0), (64, 3, 1, 0), (256, 2, 1, 30), (96, 2, 1, 0)])
+def test_chain_cfar_range_segments_like_fun_CFARflag(lib, P, C, B, mti):
+    """The three-segment waveform with the CFAR confined to each segment (CW/main_cfar.m:56-58,142-161): range windows do not
+    straddle segment borders, columns beyond the last segment stay empty.  Fused (P=64, 16 lanes), shared-memory and generic paths."""
+    R = 1031
+    segments = [(0, 82), (82, 318), (318, 868)]
+    p2, p3 = mcode.load_pulse_literals()
+    raw, _ = synth.s3_batch(B, P=P, R=R, C=C, n_targets=4, r_lo=20, r_hi=R - 80, seed0=77 + P)
+    cfar = (5, 7, 5.0, 0, 5, 7, 5.0, 0, 0, 1)
+    base = vec.chain(raw, B, P, R, C, ("lss_mp", p2, p3), cfar, mti_lag=mti, near_tol=RTOL)
+    want = _segmented_cfar_oracle(base["rdm"], cfar, segments)
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_mp(R, p2, p3), cfar, mti_lag=mti, max_det=1 << 20) as ctx:
+        ctx.set_cfar_segments(segments)
+        rdm, dets, n = ctx.chain(raw, B)
+        _close(rdm, base["rdm"])
+        _compare_flags(dets, want, B, C, P, R, lib)
+        assert not np.any(dets["r"] >= 868)
+        # the un-segmented result differs (windows straddle the borders) and is restored by an empty list
+        ctx.set_cfar_segments([])
+        _, dets0, _ = ctx.chain(raw, B)
+        _compare_flags(dets0, base, B, C, P, R, lib)
+        assert np.any(dets0["r"] >= 868)
+        # a segment shorter than the range windows: Function_CFAR1D_sub_fixCells indexes out of bounds -- but, as in the
+        # M-code, only when a velocity hit falls into that segment (the range stage runs per hit, executeCFAR.m:45-61)
+        ctx.set_cfar_segments([(0, 20), (20, 868)])
+        # cells 8..11 of a 20-cell segment fit neither window (ref 5 + guard 7 on both sides): hits at columns 7..12 test one
+        if want["flagV"][..., 7:13].any():
+            with pytest.raises(lib.MatlabIndexError):
+                ctx.chain(raw, B)
+        else:
+            ctx.chain(raw, B)
+        with pytest.raises(lib.RadarB200Error):
+            ctx.set_cfar_segments([(0, 100), (50, 200)])
