@@ -118,6 +118,20 @@ int rb200_create(rb200_ctx** out, int device, const rb200_config* cfg);
 int rb200_destroy(rb200_ctx* ctx);
 const char* rb200_last_error(const rb200_ctx* ctx);           /* NULL ctx -> last create() error    */
 int rb200_get_config(const rb200_ctx* ctx, rb200_config* out);
+
+/* One process-wide, reference-counted context per device (default configuration) for hosts that load several thin
+ * gateways into one process: every MEX gateway of mex/ (one binary per M-function name, e.g. executeCFAR of
+ * CW/main_cfar.m:90 and fun_MTD_produce of MP/main_produce_dataset_win_xzr.m:37 in one MATLAB session) acquires THIS
+ * context instead of creating a private one, so a session holds one CUDA context, one set of device scratch and one plan
+ * cache.  acquire: creates on first use, otherwise bumps the count; release: destroys the context at count 0.
+ * Same single-thread rule as any context (the interpreter calls mexFunction on its main thread).                      */
+int rb200_shared_context_acquire(rb200_ctx** out, int device);
+int rb200_shared_context_release(int device);
+/* Opaque 64-bit tag naming the waveform plan resident in a context (0 = unknown).  rb200_set_waveform clears it; a caller
+ * that built the plan stores its own hash and can later tell -- across gateways sharing the context -- whether the plan
+ * it needs is still the resident one.                                                                                  */
+int rb200_set_plan_tag(rb200_ctx* ctx, uint64_t tag);
+uint64_t rb200_get_plan_tag(const rb200_ctx* ctx);
 int rb200_set_cfar(rb200_ctx* ctx, const rb200_config* cfg);
 
 /* Range segments of the chain's CFAR = the local function fun_CFARflag of CW/main_cfar.m:142-161 (columns 1:82, 83:318,

@@ -4,8 +4,8 @@
  *  and is a thin marshalling layer over the C ABI of libradar_b200.so:
  *   - inputs are borrowed, read-only, MATLAB double (split real/imag, column-major);
  *   - outputs are allocated with mxCreateDoubleMatrix and owned by the interpreter;
- *   - one lazily created rb200 context (device RB200_DEVICE or 0) lives across calls and is
- *     destroyed in mexAtExit;
+ *   - one lazily acquired reference to the library's shared context (device RB200_DEVICE or 0) lives across
+ *     calls and is released in mexAtExit; all gateways of a session share that one context;
  *   - errors the M-code would raise become mexErrMsgIdAndTxt("radar_b200:<stage>:<what>", ...);
  *     because that call longjmps, every C++ temporary is released before it is reached
  *     (the RB_FAIL macro is only used at points where no non-trivial destructor is pending).
@@ -23,24 +23,21 @@
 #include "../include/radar_b200.h"
 #include "rb200_waveform_literals.h"
 
+/* The context is the library's process-wide shared one (rb200_shared_context_acquire): every gateway binary loaded into
+ * the session uses the same CUDA context, device scratch and plan cache; this translation unit only holds a reference. */
 static rb200_ctx* g_ctx = NULL;
-static char g_plan_key[64] = "";          /* which waveform plan is resident in the context */
-static double* g_plan_taps = NULL;        /* hash source of the cached plan's pulses */
-static size_t g_plan_ntaps = 0;
+static int g_dev = 0;
 
 static void rb_shutdown(void) {
-    if (g_ctx) rb200_destroy(g_ctx);
+    if (g_ctx) rb200_shared_context_release(g_dev);
     g_ctx = NULL;
-    g_plan_key[0] = 0;
-    free(g_plan_taps);
-    g_plan_taps = NULL;
-    g_plan_ntaps = 0;
 }
 
 static rb200_ctx* rb_context(void) {
     if (!g_ctx) {
-        const char* dev = getenv("RB200_DEVICE");
-        if (rb200_create(&g_ctx, dev ? atoi(dev) : 0, NULL) != RB200_OK) {
+        const char* dev = getenv("RB200_DEVICE");      /* once per gateway, at its first call */
+        g_dev = dev ? atoi(dev) : 0;
+        if (rb200_shared_context_acquire(&g_ctx, g_dev) != RB200_OK) {
             g_ctx = NULL;
             mexErrMsgIdAndTxt("radar_b200:init:noDevice", "%s", rb200_last_error(NULL));
         }
@@ -100,28 +97,32 @@ typedef struct {
     int n2, n3;
 } rb_pulses;
 
+/* FNV-1a over the plan key and the pulses: the tag stored in the (shared) context names the resident plan */
+static uint64_t rb_plan_tag(const char* key, const rb_pulses* p) {
+    uint64_t h = 1469598103934665603ull;
+    const double zero = 0.0;
+    size_t i;
+    int k;
+#define RB_MIX(ptr, n) do { const unsigned char* b__ = (const unsigned char*)(ptr); size_t j__; \
+        for (j__ = 0; j__ < (size_t)(n); ++j__) { h ^= b__[j__]; h *= 1099511628211ull; } } while (0)
+    RB_MIX(key, strlen(key));
+    for (k = 0; k < 2; ++k) {
+        const double* re = k ? p->p3re : p->p2re;
+        const double* im = k ? p->p3im : p->p2im;
+        const int n = k ? p->n3 : p->n2;
+        RB_MIX(&n, sizeof n);
+        for (i = 0; i < (size_t)n; ++i) { RB_MIX(re + i, sizeof(double)); RB_MIX(im ? im + i : &zero, sizeof(double)); }
+    }
+#undef RB_MIX
+    return h ? h : 1;
+}
+
 static int rb_same_plan(const char* key, const rb_pulses* p) {
-    size_t need = (size_t)2 * (p->n2 + p->n3), i, k = 0;
-    if (strcmp(key, g_plan_key) != 0 || need != g_plan_ntaps) return 0;
-    for (i = 0; i < (size_t)p->n2; ++i) {
-        if (g_plan_taps[k++] != p->p2re[i]) return 0;
-        if (g_plan_taps[k++] != (p->p2im ? p->p2im[i] : 0.0)) return 0;
-    }
-    for (i = 0; i < (size_t)p->n3; ++i) {
-        if (g_plan_taps[k++] != p->p3re[i]) return 0;
-        if (g_plan_taps[k++] != (p->p3im ? p->p3im[i] : 0.0)) return 0;
-    }
-    return 1;
+    return rb200_get_plan_tag(rb_context()) == rb_plan_tag(key, p);
 }
 
 static void rb_remember_plan(const char* key, const rb_pulses* p) {
-    size_t need = (size_t)2 * (p->n2 + p->n3), i, k = 0;
-    free(g_plan_taps);
-    g_plan_taps = (double*)malloc((need ? need : 1) * sizeof(double));
-    g_plan_ntaps = need;
-    for (i = 0; i < (size_t)p->n2; ++i) { g_plan_taps[k++] = p->p2re[i]; g_plan_taps[k++] = p->p2im ? p->p2im[i] : 0.0; }
-    for (i = 0; i < (size_t)p->n3; ++i) { g_plan_taps[k++] = p->p3re[i]; g_plan_taps[k++] = p->p3im ? p->p3im[i] : 0.0; }
-    snprintf(g_plan_key, sizeof g_plan_key, "%s", key);
+    rb200_set_plan_tag(rb_context(), rb_plan_tag(key, p));
 }
 
 static void rb_fir_taps(double* b) {   /* filter_coef / max(filter_coef), MP/fun_lss_pulse_compression.m:21-22 */
@@ -150,7 +151,6 @@ static void rb_plan_mp(int n, const rb_pulses* p) {
     s[1].kind = RB200_SEG_MF; s[1].align = RB200_ALIGN_LEADING_EDGE; s[1].n_taps = p->n2; s[1].taps_re = p->p2re; s[1].taps_im = p->p2im; s[1].scale = 1.0;
     s[2].in_start = 324; s[2].in_len = n - 324; s[2].out_start = 324; s[2].out_len = n - 324;
     s[2].kind = RB200_SEG_MF; s[2].align = RB200_ALIGN_LEADING_EDGE; s[2].n_taps = p->n3; s[2].taps_re = p->p3re; s[2].taps_im = p->p3im; s[2].scale = 1.0;
-    g_plan_key[0] = 0;
     rb_check(rb200_set_waveform(ctx, s, 3), "pc");
     rb_remember_plan(key, p);
 }
@@ -173,7 +173,6 @@ static void rb_plan_mtd(int n, const rb_pulses* p, int p1, int p2, int p3) {
     s[1].kind = RB200_SEG_MF; s[1].align = RB200_ALIGN_LEADING_EDGE; s[1].n_taps = p->n2; s[1].taps_re = p->p2re; s[1].taps_im = p->p2im; s[1].scale = 1.0;
     s[2].in_start = p1 + p2; s[2].in_len = n - p1 - p2; s[2].out_start = p1 + p2; s[2].out_len = p3;
     s[2].kind = RB200_SEG_MF; s[2].align = RB200_ALIGN_LEADING_EDGE; s[2].n_taps = p->n3; s[2].taps_re = p->p3re; s[2].taps_im = p->p3im; s[2].scale = 1.0;
-    g_plan_key[0] = 0;
     rb_check(rb200_set_waveform(ctx, s, 3), "pc");
     rb_remember_plan(key, p);
 }

@@ -64,6 +64,7 @@ EXPORTS = [
     "rb200_chain_enqueue", "rb200_chain_fetch", "rb200_debug_fetch_pc", "rb200_last_device_ms",
     "rb200_last_launch_count", "rb200_set_dbf", "rb200_set_cfar_segments", "rb200_set_stage_timing", "rb200_get_stage_ms", "rb200_unpack_dbf24", "rb200_chain_dbf24", "rb200_mtd_produce_windows_z", "rb200_dmx_process_z", "rb200_motion_para_measure_d", "rb200_reader_open", "rb200_reader_close",
     "rb200_reader_last_error", "rb200_reader_state", "rb200_reader_next_frame_ddc", "rb200_reader_next_frame_dbf24",
+    "rb200_shared_context_acquire", "rb200_shared_context_release", "rb200_set_plan_tag", "rb200_get_plan_tag",
 ]
 
 _lib = None
@@ -124,6 +125,11 @@ def load():
     lib.rb200_reader_state.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
     lib.rb200_reader_next_frame_ddc.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rb200_reader_next_frame_dbf24.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.rb200_shared_context_acquire.argtypes = [C.POINTER(vp), C.c_int]
+    lib.rb200_shared_context_release.argtypes = [C.c_int]
+    lib.rb200_set_plan_tag.argtypes = [vp, C.c_uint64]
+    lib.rb200_get_plan_tag.argtypes = [vp]
+    lib.rb200_get_plan_tag.restype = C.c_uint64
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

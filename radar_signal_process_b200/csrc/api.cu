@@ -139,8 +139,32 @@ struct MtdPlan {
 
 }  // namespace
 
+// Experiment switches, read from the environment ONCE in rb200_create -- never on a call path.
+struct EnvSwitches {
+    int pc_nt = 0;              // RB200_PC_NT
+    int chunk = 0;              // RB200_CHUNK
+    int slots = 0;              // RB200_SLOTS (0 = default)
+    bool no_tma = false, no_tma_mtd = false, no_fused = false, no_fused_v = false, mega = false, no_cfar_tile = false;
+    bool no_onepass = false;    // RB200_NO_ONEPASS: keep the PC intermediate in HBM (the round-1 slot pipeline)
+    void read() {
+        auto flag = [](const char* n) { const char* v = getenv(n); return v != nullptr && v[0] != 0 && !(v[0] == '0' && v[1] == 0); };
+        auto num = [](const char* n) { const char* v = getenv(n); return v ? atoi(v) : 0; };
+        pc_nt = num("RB200_PC_NT");
+        chunk = num("RB200_CHUNK");
+        slots = num("RB200_SLOTS");
+        no_tma = flag("RB200_NO_TMA");
+        no_tma_mtd = flag("RB200_NO_TMA_MTD");
+        no_fused = flag("RB200_NO_FUSED");
+        no_fused_v = flag("RB200_NO_FUSED_V");
+        mega = flag("RB200_MEGA");
+        no_cfar_tile = flag("RB200_NO_CFAR_TILE");
+        no_onepass = flag("RB200_NO_ONEPASS");
+    }
+};
+
 struct rb200_ctx {
     int device = 0;
+    EnvSwitches env;
     cudaStream_t stream = nullptr;
     rb200_config cfg;
     std::string err;
@@ -148,6 +172,9 @@ struct rb200_ctx {
     CfarSegs cfar_segs = {};       // rb200_set_cfar_segments (fun_CFARflag); n = 0: whole range axis
     Plan dmx_plan;                 // private plan of rb200_dmx_process_z (never touches the caller's waveform)
     unsigned long long dmx_key = 0;
+    uint64_t plan_tag = 0;         // rb200_set_plan_tag / rb200_get_plan_tag; cleared by rb200_set_waveform
+    Plan pcz_plan;                 // cached plan of rb200_pulse_compression_z, keyed on (L, M, hash of the taps)
+    unsigned long long pcz_key = 0;
     std::map<std::pair<int, long long>, MtdPlan*> mtd_plans;
     DevBuf gain;
     int gain_n = 0;
@@ -223,10 +250,9 @@ static int fail(rb200_ctx* c, int code, const char* msg) {
 // ---------------------------------------------------------------------------------------------
 // plans
 // ---------------------------------------------------------------------------------------------
-static int choose_nt(int L) {
-    const char* env = getenv("RB200_PC_NT");
-    if (env) {
-        const int nt = atoi(env);
+static int choose_nt(int L, int forced_nt) {
+    if (forced_nt) {
+        const int nt = forced_nt;
         if ((nt == 256 || nt == 512 || nt == 4096) && nt - L + 1 >= nt / 8) return nt;
     }
     // estimated butterfly flops per transformed point (forward + inverse + spectrum multiply)
@@ -296,7 +322,7 @@ static int build_plan(rb200_ctx* ctx, Plan& plan, const rb200_segment* segs, int
         } else {
             return fail(ctx, RB200_ERR_ARG, "set_waveform: unknown segment kind");
         }
-        sp.nt = s.kind == RB200_SEG_MF_CIRC ? s.out_len : choose_nt(L);
+        sp.nt = s.kind == RB200_SEG_MF_CIRC ? s.out_len : choose_nt(L, ctx->env.pc_nt);
         sp.d.t_off = (int)taps_all.size();
         for (int k = 0; k < L; ++k) {
             const cd t = corr_taps[i][k] * s.scale;    // direct kernel multiplies by conj(t) -> fold real scale
@@ -400,7 +426,7 @@ static int run_pc(rb200_ctx* ctx, const Plan& plan, bool wire, const void* in, f
         const int lt = pc_tile_lanes(c.nt, wire);
         const int n_groups = wire ? n_groups_wire : (n_lines + lt - 1) / lt;
         if (n_groups <= 0) continue;
-        if (wire && C == 16 && c.nt == 256 && plan.h_entries <= 2048 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && !getenv("RB200_NO_TMA"))
+        if (wire && C == 16 && c.nt == 256 && plan.h_entries <= 2048 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && !ctx->env.no_tma)
             CK(ctx, launch_pc_fft_tma(p, c.n_tiles, n_groups, ctx->n_sms, ctx->pc_ctas_per_sm, plan.h_entries, st));
         else CK(ctx, launch_pc_fft(c.nt, wire, p, c.n_tiles, n_groups, st));
         ctx->launches++;
@@ -608,6 +634,7 @@ extern "C" int rb200_create(rb200_ctx** out, int device, const rb200_config* cfg
     }
     if (validate_cfar(c, k)) { g_create_error = c->err; delete c; return RB200_ERR_ARG; }
     cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device);
+    c->env.read();
     if (const char* e1 = getenv("RB200_PC_CTAS")) c->pc_ctas_per_sm = atoi(e1);
     if (const char* e2 = getenv("RB200_MTD_CTAS")) c->mtd_ctas_per_sm = atoi(e2);
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -638,6 +665,7 @@ extern "C" int rb200_destroy(rb200_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->plan.release();
     c->dmx_plan.release();
+    c->pcz_plan.release();
     for (auto& kv : c->mtd_plans) {
         kv.second->window.release();
         kv.second->tw.release();
@@ -664,6 +692,40 @@ extern "C" int rb200_destroy(rb200_ctx* c) {
     return RB200_OK;
 }
 
+// ---- process-wide shared contexts (one per device), reference counted --------------------------------------------
+namespace {
+struct SharedCtx { rb200_ctx* ctx = nullptr; int refs = 0; };
+SharedCtx g_shared[64];
+}
+extern "C" int rb200_shared_context_acquire(rb200_ctx** out, int device) {
+    if (!out || device < 0 || device >= 64) { g_create_error = "rb200_shared_context_acquire: bad argument"; return RB200_ERR_ARG; }
+    SharedCtx& s = g_shared[device];
+    if (!s.ctx) {
+        int rc = rb200_create(&s.ctx, device, nullptr);
+        if (rc) { s.ctx = nullptr; *out = nullptr; return rc; }
+        s.refs = 0;
+    }
+    ++s.refs;
+    *out = s.ctx;
+    return RB200_OK;
+}
+extern "C" int rb200_shared_context_release(int device) {
+    if (device < 0 || device >= 64) return RB200_ERR_ARG;
+    SharedCtx& s = g_shared[device];
+    if (!s.ctx || s.refs <= 0) return RB200_ERR_ARG;
+    if (--s.refs == 0) {
+        rb200_destroy(s.ctx);
+        s.ctx = nullptr;
+    }
+    return RB200_OK;
+}
+extern "C" int rb200_set_plan_tag(rb200_ctx* c, uint64_t tag) {
+    if (!c) return RB200_ERR_ARG;
+    c->plan_tag = tag;
+    return RB200_OK;
+}
+extern "C" uint64_t rb200_get_plan_tag(const rb200_ctx* c) { return c ? c->plan_tag : 0; }
+
 extern "C" const char* rb200_last_error(const rb200_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int rb200_get_config(const rb200_ctx* c, rb200_config* out) {
@@ -687,6 +749,7 @@ extern "C" int rb200_set_cfar(rb200_ctx* c, const rb200_config* cfg) {
 extern "C" int rb200_set_waveform(rb200_ctx* c, const rb200_segment* segs, int nseg) {
     if (!c) return RB200_ERR_ARG;
     cudaSetDevice(c->device);
+    c->plan_tag = 0;
     return build_plan(c, c->plan, segs, nseg);
 }
 
@@ -770,37 +833,47 @@ extern "C" int rb200_pulse_compression_z(rb200_ctx* c, const double* s0_re, cons
         return RB200_OK;
     }
     // full convolution with conj(flip(s0)): y[m] = sum_j x[m-(L-1)+j] conj(s0[j])  (MP/fun_pulse_compression.m:4,19-22)
-    Plan tmp;
-    rb200_segment s;
-    memset(&s, 0, sizeof s);
-    s.in_start = 0; s.in_len = M; s.out_start = 0; s.out_len = N;
-    s.kind = RB200_SEG_MF; s.align = RB200_ALIGN_LEADING_EDGE;
-    s.n_taps = L; s.taps_re = s0_re; s.taps_im = s0_im; s.scale = 1.0;
-    int rc = build_plan(c, tmp, &s, 1);
-    if (rc) { tmp.release(); return rc; }
-    tmp.segs[0].d.pre = L - 1;
-    const double *dre, *dim;
-    rc = upload_z(c, echo_re, echo_im, M, &dre, &dim);
-    if (rc) { tmp.release(); return rc; }
-    cudaError_t e = c->s_a.ensure((size_t)M * sizeof(float2));
-    if (e == cudaSuccess) e = c->s_b.ensure((size_t)N * sizeof(float2));
-    if (e == cudaSuccess) e = c->s_out_re.ensure(N * sizeof(double));
-    if (e == cudaSuccess) e = c->s_out_im.ensure(N * sizeof(double));
-    if (e == cudaSuccess) e = launch_z_to_planar(dre, dim, c->s_a.as<float2>(), 1, M, c->stream);
-    if (e != cudaSuccess) { tmp.release(); c->err = cudaGetErrorString(e); return RB200_ERR_CUDA; }
-    c->launches++;
-    rc = run_pc(c, tmp, false, c->s_a.p, c->s_b.as<float2>(), M, N, 1, 1, 0, 1, nullptr, c->stream);
-    if (!rc) {
-        e = launch_planar_to_z(c->s_b.as<float2>(), c->s_out_re.as<double>(), c->s_out_im.as<double>(), 1, N, c->stream);
-        c->launches++;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out_re, c->s_out_re.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out_im, c->s_out_im.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = RB200_ERR_CUDA; }
+    // The plan (reference spectrum, tiles, twiddles) is cached on (L, M, taps): a caller looping over PRTs with one pulse --
+    // MP/fun_lss_pulse_compression.m:24-37 does exactly that -- pays for it once, not per call like the M-code (:20).
+    unsigned long long key = 1469598103934665603ull;
+    auto mix = [&](const void* ptr, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(ptr);
+        for (size_t i = 0; i < n; ++i) { key ^= b[i]; key *= 1099511628211ull; }
+    };
+    mix(&L, sizeof L);
+    mix(&M, sizeof M);
+    mix(s0_re, (size_t)L * sizeof(double));
+    if (s0_im) mix(s0_im, (size_t)L * sizeof(double));
+    else { const int z = 0; mix(&z, sizeof z); }
+    Plan& plan = c->pcz_plan;
+    if (!plan.valid || c->pcz_key != key) {
+        rb200_segment s;
+        memset(&s, 0, sizeof s);
+        s.in_start = 0; s.in_len = M; s.out_start = 0; s.out_len = N;
+        s.kind = RB200_SEG_MF; s.align = RB200_ALIGN_LEADING_EDGE;
+        s.n_taps = L; s.taps_re = s0_re; s.taps_im = s0_im; s.scale = 1.0;
+        int rc = build_plan(c, plan, &s, 1);
+        if (rc) { plan.release(); return rc; }
+        plan.segs[0].d.pre = L - 1;
+        c->pcz_key = key;
     }
-    cudaStreamSynchronize(c->stream);
-    tmp.release();
-    return rc;
+    const double *dre, *dim;
+    int rc = upload_z(c, echo_re, echo_im, M, &dre, &dim);
+    if (rc) return rc;
+    CK(c, c->s_a.ensure((size_t)M * sizeof(float2)));
+    CK(c, c->s_b.ensure((size_t)N * sizeof(float2)));
+    CK(c, c->s_out_re.ensure(N * sizeof(double)));
+    CK(c, c->s_out_im.ensure(N * sizeof(double)));
+    CK(c, launch_z_to_planar(dre, dim, c->s_a.as<float2>(), 1, M, c->stream));
+    c->launches++;
+    rc = run_pc(c, plan, false, c->s_a.p, c->s_b.as<float2>(), M, N, 1, 1, 0, 1, nullptr, c->stream);
+    if (rc) return rc;
+    CK(c, launch_planar_to_z(c->s_b.as<float2>(), c->s_out_re.as<double>(), c->s_out_im.as<double>(), 1, N, c->stream));
+    c->launches++;
+    CK(c, cudaMemcpyAsync(out_re, c->s_out_re.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(out_im, c->s_out_im.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RB200_OK;
 }
 
 extern "C" int rb200_lss_pulse_compression_z(rb200_ctx* c, const double* echo_re, const double* echo_im, int P, int R,
@@ -1268,17 +1341,20 @@ extern "C" int rb200_motion_para_measure_d(rb200_ctx* c, const double* mtd_sum, 
 }
 
 static int chunk_size(const rb200_ctx* c, bool host_staged = false) {
-    const char* env = getenv("RB200_CHUNK");
-    int g = env ? atoi(env) : c->cfg.chunk_cpi;
+    int g = c->env.chunk ? c->env.chunk : c->cfg.chunk_cpi;
     if (g <= 0) {
         // default: ~0.5 GB of raw+PC+RDM per chunk (S3: 8 CPIs).  Measured on B200: per-launch overheads dominate below
         // 4 CPIs per chunk and the PC intermediate is not L2-resident at any practical chunk size (profiles/README.md)
-        const double per_cpi = (double)c->cfg.n_prt * c->cfg.n_range * c->cfg.n_lanes * 16.0;
+        const double per_cpi = (double)c->cfg.n_prt * c->cfg.n_range * (c->dbf_beams ? c->dbf_beams : c->cfg.n_lanes) * 16.0;
         g = (int)std::floor(540e6 / per_cpi);
         // host buffers: the call is PCIe-bound and the first H2D / last D2H of a call cannot overlap anything, so halve
         // the chunk (measured: 2.63 k -> 2.71 k CPI/s end to end; 49 GB/s each way is the box's full-duplex ceiling)
         if (host_staged) g = std::max(1, g / 2);
     }
+    // grid.y carries (CPIs x lanes) slabs and, on the DBF path, (CPIs x PRTs) groups: keep both inside the 65535 limit
+    const int lanes = std::max(1, std::max(c->cfg.n_lanes, c->dbf_beams));
+    g = std::min(g, 65535 / lanes);
+    if (c->dbf_beams) g = std::min(g, 65535 / std::max(1, c->cfg.n_prt));
     return std::max(1, std::min(g, c->cfg.max_cpi));
 }
 
@@ -1311,10 +1387,6 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     CK(c, c->dets_v.ensure((size_t)k.max_det * sizeof(rb200_det)));
     CK(c, c->dets_2d.ensure((size_t)k.max_det * sizeof(rb200_det)));
     float* rdm_base = rdm_dev;
-    if (!rdm_base && !rdm_host) {
-        CK(c, c->rdm.ensure((size_t)G * cpi_cells * sizeof(float)));
-        rdm_base = c->rdm.as<float>();
-    }
     CfarParams cp;
     memset(&cp, 0, sizeof cp);
     cp.V = P; cp.R = R;
@@ -1330,7 +1402,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     c->launches = 0;
     CK(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(int), st));
     CK(c, cudaMemsetAsync(c->errflag.p, 0, sizeof(int), st));
-    const bool fused = !getenv("RB200_NO_FUSED") && mtd64_fused_supported(P, k.cfar_ref_v, k.cfar_guard_v, k.cfar_n0, k.mti_lag);
+    const bool fused = !c->env.no_fused && mtd64_fused_supported(P, k.cfar_ref_v, k.cfar_guard_v, k.cfar_n0, k.mti_lag);
     Mtd64Params m64;
     memset(&m64, 0, sizeof m64);
     int n_slots = 1;
@@ -1339,7 +1411,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     //      one 256-sample tile class covering the whole PRT
     if (fused && raw_dev && rdm_dev && !raw_host && !rdm_host && C == 16 && !planar_in && c->plan.valid && c->plan.classes.size() == 1 &&
         c->plan.classes[0].nt == 256 && c->plan.max_in_end <= R && c->plan.max_out_end <= R && (reinterpret_cast<uintptr_t>(raw_dev) & 15) == 0 &&
-        getenv("RB200_MEGA")) {      // opt-in: measured slower than the slot pipeline on B200 (profiles/README.md)
+        c->env.mega) {      // opt-in: measured slower than the slot pipeline on B200 (profiles/README.md)
         bool direct = false, covered = true;
         for (auto& sp : c->plan.segs) direct |= (sp.nt == 0 && sp.d.out_len > 0);
         int cur = 0;
@@ -1430,8 +1502,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         m64.max_det = k.max_det;
         m64.n_lanes = C;
         m64.segs = c->cfar_segs;
-        const char* env = getenv("RB200_SLOTS");
-        n_slots = env ? atoi(env) : 3;
+        n_slots = c->env.slots ? c->env.slots : 3;
         n_slots = std::max(1, std::min(n_slots, (int)rb200_ctx::kMaxSlots));
         if (c->stage_timing) n_slots = 1;                      // per-stage events need the chunks serialised
         n_slots = std::min(n_slots, (n_cpi + G - 1) / G);
@@ -1448,7 +1519,9 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     for (int i = 0; i < n_slots; ++i) {
         if (raw_host) CK(c, c->slots[i].raw.ensure((size_t)G * raw_cpi_bytes));
         if (planar_in) CK(c, c->slots[i].beams.ensure((size_t)G * cpi_cells * sizeof(float2)));
-        if (rdm_host) CK(c, c->slots[i].rdm.ensure((size_t)G * cpi_cells * sizeof(float)));
+        // host output, or no output at all: every slot owns the RDM of its chunk (the range stage and the detection
+        // amplitudes of chunk i read it while chunk i+1 is already being transformed on another slot stream)
+        if (rdm_host || !rdm_dev) CK(c, c->slots[i].rdm.ensure((size_t)G * cpi_cells * sizeof(float)));
     }
     CK(c, cudaEventRecord(c->ev0, st));
     if (n_slots > 1) {
@@ -1467,7 +1540,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
                                   cudaMemcpyHostToDevice, cs));
             raw_chunk = sl.raw.as<int16_t>();
         }
-        float* rdm_chunk = rdm_host ? sl.rdm.as<float>() : (rdm_dev ? rdm_base + (size_t)c0 * cpi_cells : rdm_base);
+        float* rdm_chunk = rdm_dev ? rdm_base + (size_t)c0 * cpi_cells : sl.rdm.as<float>();
         float2* pc_buf = fused ? sl.pc.as<float2>() : c->pc.as<float2>();
         const bool timed = c->stage_timing && c->stage_used + 4 <= 65536;
         if (timed) { stage_event(c, cs); c->stage_cpis.push_back(g); }
@@ -1499,7 +1572,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
             m64.dets = sl.vlist.p;
             m64.det_count = sl.count.as<int>();
             m64.colmask = sl.colmask.as<unsigned long long>();
-            if ((R % 2) == 0 && !getenv("RB200_NO_TMA_MTD")) CK(c, launch_mtd64_tma(m64, g * C, c->n_sms, c->mtd_ctas_per_sm, cs));
+            if ((R % 2) == 0 && !c->env.no_tma_mtd) CK(c, launch_mtd64_tma(m64, g * C, c->n_sms, c->mtd_ctas_per_sm, cs));
             else CK(c, launch_mtd64(m64, g * C, true, cs));
             c->launches++;
             if (timed) stage_event(c, cs);
@@ -1511,7 +1584,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
             if (cp.v_hi > cp.v_lo)
                 CK(c, cudaMemcpyAsync(c->counters.as<int>() + 2, c->counters.as<int>() + 0, sizeof(int), cudaMemcpyDeviceToDevice, cs));
             const bool fuse_v = cp.v_hi > cp.v_lo && mtd_fast_fuses_cfar(P) && (cp.v_hi - cp.v_lo) >= 2 * (cp.ref_v + cp.guard_v) &&
-                                !getenv("RB200_NO_FUSED_V");
+                                !c->env.no_fused_v;
             FusedV fvp = {&cp, (float)k.cfar_t_v, c->dets_v.p, c->counters.as<int>() + 0, c->vmask.as<uint32_t>(), c->errflag.as<int>()};
             rc = run_mtd(c, pc_buf, rdm_chunk, P, R, R, R, g * C, k.kaiser_beta, k.zero_v_div, k.mti_lag, cs, fuse_v ? &fvp : nullptr);
             if (rc) return rc;

@@ -236,7 +236,8 @@ static cudaError_t run_cfar(const T* rdm, const CfarParams& p, T t_r, T t_v, int
     const int rows_per_seg = (nv + segs - 1) / segs;
     dim3 grid(col_blocks, n_slabs, (nv + rows_per_seg - 1) / rows_per_seg);
     const int H = p.ref_v + p.guard_v;
-    if (ROWMAJOR && sizeof(T) == 4 && !flagv && H <= 48 && !getenv("RB200_NO_CFAR_TILE")) {
+    static const bool no_tile = getenv("RB200_NO_CFAR_TILE") != nullptr;     // experiment switch, read once per process
+    if (ROWMAJOR && sizeof(T) == 4 && !flagv && H <= 48 && !no_tile) {
         const size_t smem = (size_t)(RB_CFAR_TILE_ROWS + 2 * H) * 128 * sizeof(float);
         static size_t configured[64] = {};
         cudaError_t ce = ensure_dynamic_smem(cfar_v_tiled_kernel, smem, configured);

@@ -59,19 +59,21 @@ __device__ __forceinline__ void mtd64_column(float2 (&v)[64], const Mtd64Params&
     // ---- velocity-axis CA-CFAR on the register column (tested rows N0+1 .. 63-N0) ----
     constexpr int NV = P - 2 * N0 - 1;
     static_assert(!CFAR || NV >= 2 * (REF + GUARD), "velocity axis shorter than 2*(ref+guard)");
-    float pre[NV + 1];
-    pre[0] = 0.f;
-#pragma unroll
-    for (int y = 0; y < NV; ++y) pre[y + 1] = pre[y] + mag[N0 + 1 + y];
+    // window sums are taken directly from the REF cells (compile-time indices, registers only): a running prefix over the
+    // whole column would quantise the sums behind a strong target to the ulp of the peak
     unsigned long long hits = 0ull;
 #pragma unroll
     for (int y = 0; y < NV; ++y) {
         const int l1 = y - GUARD - REF;
-        const int r2 = y + GUARD + REF;
+        const int r1 = y + GUARD + 1;
         const bool okL = l1 >= 0;
-        const bool okR = r2 <= NV - 1;
-        const float sl = okL ? pre[y - GUARD] - pre[okL ? l1 : 0] : 0.f;
-        const float sr = okR ? pre[okR ? r2 + 1 : 0] - pre[okR ? y + GUARD + 1 : 0] : 0.f;
+        const bool okR = r1 + REF - 1 <= NV - 1;
+        float sl = 0.f, sr = 0.f;
+#pragma unroll
+        for (int j = 0; j < REF; ++j) {
+            if (okL) sl += mag[N0 + 1 + (okL ? l1 + j : 0)];
+            if (okR) sr += mag[N0 + 1 + (okR ? r1 + j : 0)];
+        }
         const float a = okL ? sl : sr;
         const float b = okR ? sr : sl;
         const float mu = p.meth_v == 0 ? fmaxf(a, b) : fminf(a, b);

@@ -8,7 +8,9 @@
 // MATLAB matrix.  The reference's file-index behaviour is reproduced exactly, including the double increment
 // after a read that ends exactly at the end of a file (read_continuous_file_stream.m:148 then :48), which
 // skips the next file; RB200_READER_NO_SKIP_QUIRK=1 switches that off.
+#include <algorithm>
 #include <cstdint>
+#include <exception>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -159,6 +161,15 @@ static int next_frame(rb200_reader* r, int want_type, int n_prt, int n_range, in
         else if (data_type == 1) sig = (long long)pulse_data_num * channel_num * 2 * 2;
         else sig = (long long)pulse_data_num * channel_num * 6 + (long long)pulse_data_num * (8 - (6 * channel_num) % 8);
         const long long padded = sig + ((sig % 64) ? 64 - sig % 64 : 0);                                         // :115-119
+        // The head is unvalidated capture data: a corrupt pulse_data_num / channel_num must not turn into a terabyte
+        // allocation.  A payload far beyond the configured geometry can only end in the short read the reference gets
+        // from fread (:122-127), so report end-of-stream without allocating.
+        const long long expect = (long long)n_range * n_channels * 8 + 64;
+        if (padded > std::max<long long>(4 * expect, 1ll << 20)) {
+            *end_of_stream = 1;
+            r->err = "PRT head announces a payload far larger than the configured geometry (corrupt capture?)";
+            return RB200_OK;
+        }
         buf.resize((size_t)padded);
         if (stream_read(r, buf.data(), padded, &eos) < padded || eos) { *end_of_stream = 1; return RB200_OK; }   // :122-127
         if ((int)data_type != want_type) {
@@ -187,12 +198,24 @@ static int next_frame(rb200_reader* r, int want_type, int n_prt, int n_range, in
 extern "C" int rb200_reader_next_frame_ddc(rb200_reader* r, int n_prt, int n_range, int n_channels, int16_t* raw_out,
                                            uint32_t* frame_no, uint16_t* servo_angle, uint64_t* timer_cnt,
                                            int* prts_read, int* end_of_stream) {
-    return next_frame(r, 1, n_prt, n_range, n_channels, reinterpret_cast<uint8_t*>(raw_out), frame_no, servo_angle, timer_cnt, prts_read,
-                      end_of_stream);
+    try {
+        return next_frame(r, 1, n_prt, n_range, n_channels, reinterpret_cast<uint8_t*>(raw_out), frame_no, servo_angle, timer_cnt, prts_read,
+                          end_of_stream);
+    } catch (const std::exception& e) {          // no C++ exception crosses the C ABI
+        if (r) r->err = std::string("rb200_reader_next_frame_ddc: ") + e.what();
+        if (end_of_stream) *end_of_stream = 1;
+        return RB200_ERR_ARG;
+    }
 }
 
 extern "C" int rb200_reader_next_frame_dbf24(rb200_reader* r, int n_prt, int n_range, int n_channels, uint8_t* payload_out,
                                              uint32_t* frame_no, uint16_t* servo_angle, uint64_t* timer_cnt,
                                              int* prts_read, int* end_of_stream) {
-    return next_frame(r, 2, n_prt, n_range, n_channels, payload_out, frame_no, servo_angle, timer_cnt, prts_read, end_of_stream);
+    try {
+        return next_frame(r, 2, n_prt, n_range, n_channels, payload_out, frame_no, servo_angle, timer_cnt, prts_read, end_of_stream);
+    } catch (const std::exception& e) {
+        if (r) r->err = std::string("rb200_reader_next_frame_dbf24: ") + e.what();
+        if (end_of_stream) *end_of_stream = 1;
+        return RB200_ERR_ARG;
+    }
 }

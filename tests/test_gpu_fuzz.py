@@ -62,3 +62,6 @@ def test_chain_random_configuration(lib, seed):
     bad_v = (flagv != out["flagV"]) & ~out["nearV"]
     bad_2 = (flag != out["flag"]) & ~out["near"]
     assert bad_v.sum() == 0 and bad_2.sum() == 0, (k, int(bad_v.sum()), int(bad_2.sum()))
+    # the excused (near-threshold) differences are themselves bounded: at most 1e-3 of the cells
+    n_diff = int((flagv != out["flagV"]).sum()), int((flag != out["flag"]).sum())
+    assert max(n_diff) <= 1e-3 * flag.size, (k, n_diff, flag.size)

@@ -139,3 +139,30 @@ def test_mex_DMX_frame_process():
     with pytest.raises(MexError) as e:
         Mex("DMX_frame_process")(left, right, n_short, mcode.FILTER_COEF_INT, mf, 500, win, mtd_fft, n0, nargout=4)
     assert e.value.ident == "radar_b200:dmx:unsupported"
+
+
+def test_mex_gateways_share_one_context_and_track_the_resident_plan():
+    """All gateway binaries of a session hold references to ONE library context (rb200_shared_context_acquire).  A plan set
+    through one gateway is recognised -- or replaced -- by another through the context's plan tag: interleaving
+    fun_MTD_produce (1-arg plan, 1031 columns) with fun_lss_pulse_compression on a different geometry and back again
+    must keep giving the oracle's results."""
+    import ctypes
+    import radar_signal_process_b200 as rsp
+    rng = np.random.default_rng(9)
+    p2, p3 = mcode.load_pulse_literals()
+    echo_a = np.rint(100 * _rc(rng, 8, 1031))
+    echo_b = np.rint(100 * _rc(rng, 4, 1024))
+    want_a = mcode.fun_MTD_produce_mp(echo_a)
+    want_b = mcode.fun_lss_pulse_compression_mp(echo_b, None, p2, p3)
+    for _ in range(2):
+        _close(Mex("fun_MTD_produce")(echo_a), want_a)
+        _close(Mex("fun_lss_pulse_compression")(echo_b, 0, mcode.pulse1_mp(), p2, p3), want_b)
+        _close(Mex("fun_lss_pulse_compression")(echo_a, 0, mcode.pulse1_mp(), p2, p3), mcode.fun_lss_pulse_compression_mp(echo_a, None, p2, p3))
+    # the library hands every caller of the shared context the same handle
+    lib = rsp.load()
+    h1, h2 = ctypes.c_void_p(), ctypes.c_void_p()
+    assert lib.rb200_shared_context_acquire(ctypes.byref(h1), 0) == 0
+    assert lib.rb200_shared_context_acquire(ctypes.byref(h2), 0) == 0
+    assert h1.value == h2.value and h1.value
+    assert lib.rb200_get_plan_tag(h1) != 0
+    assert lib.rb200_shared_context_release(0) == 0 and lib.rb200_shared_context_release(0) == 0

@@ -14,6 +14,9 @@ from oracle import mcode, synth, vec
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-4
+NEAR_FRAC = 1e-3        # differing flags (all of them excused by a near-threshold mask) per cell, upper bound
+NEAR_MASK_FRAC = 0.25   # cells the oracle may mark "near a threshold or a tie" (zeroed 0-v rows tie exactly and are dilated over the
+                        # 2-D election: 1.7 % of S3, 11.5 % of the S1 crop); what is bounded tightly is the number of cells that DIFFER
 
 
 def _rand_c(rng, *shape):
@@ -156,9 +159,15 @@ def test_fun_MTD_produce_S1(lib):
         fg[:, a - 1:b] = f
     # same input (the GPU RDM) through the oracle must give identical flags: double path is exact
     assert np.array_equal(fg, vec.cfar_flag_segments(crop_g, args))
-    # against the oracle's own RDM only near-threshold cells may differ
-    fw = vec.cfar_flag_segments(crop_w, args)
-    print("S1 flags: gpu %d oracle %d differing %d" % (fg.sum(), fw.sum(), (fg != fw).sum()))
+    # against the oracle's own RDM only near-threshold cells may differ (CW/main_cfar.m:86-93,142-161), and few of them
+    want_f = _segmented_cfar_oracle(crop_w, args, ((0, 82), (82, 318), (318, 868)))
+    diff = fg.astype(bool) != want_f["flag"]
+    unexcused = diff & ~want_f["near"]
+    print("S1 flags: gpu %d oracle %d differing %d unexcused %d near-mask %d" %
+          (fg.sum(), want_f["flag"].sum(), diff.sum(), unexcused.sum(), want_f["near"].sum()))
+    assert np.array_equal(want_f["flag"], vec.cfar_flag_segments(crop_w, args).astype(bool))
+    assert unexcused.sum() == 0
+    assert diff.sum() <= NEAR_FRAC * fg.size and want_f["near"].sum() <= NEAR_MASK_FRAC * fg.size
 
 
 def test_fun_MTD_produce_S2_and_cfar(lib):
@@ -254,6 +263,12 @@ def _compare_flags(got_dets, out, B, C, V, R, lib):
           (flagv.sum(), out["flagV"].sum(), dv.sum(), bad_v.sum(), flag.sum(), out["flag"].sum(), d2.sum(), bad_2.sum()))
     assert bad_v.sum() == 0
     assert bad_2.sum() == 0
+    # the excused set itself is bounded: cells that differ (all of them inside a near-threshold mask, asserted above) may be
+    # at most 1e-3 of all cells -- a kernel that pushed 5 % of the cells across a threshold fails here even if excused
+    cells = flag.size
+    assert dv.sum() <= NEAR_FRAC * cells and d2.sum() <= NEAR_FRAC * cells, (int(dv.sum()), int(d2.sum()), cells)
+    assert out["nearV"].sum() <= NEAR_MASK_FRAC * cells and out["near"].sum() <= NEAR_MASK_FRAC * cells, \
+        (int(out["nearV"].sum()), int(out["near"].sum()), cells)
     return int(dv.sum()), int(d2.sum())
 
 
@@ -350,6 +365,54 @@ def test_chain_full_size_properties(lib):
     want = np.zeros(R, dtype=complex)
     want[1000 - 66:1001] = np.conj(ref[::-1])
     _close(pc[5, 17], want)
+
+
+def test_chain_bench_configuration_64_cpis_spot_checked(lib):
+    """The exact bench configuration (64 CPIs of 64 x 4096 x 16 per call, default chunk size, default slot streams, host
+    buffers) with four randomly chosen CPIs compared cell by cell against the oracle (RDM and both flag matrices)."""
+    P, R, C, B, D = 64, 4096, 16, 64, 8
+    distinct, _ = synth.s3_batch(D)
+    order = np.random.default_rng(64).permutation(B) % D            # every distinct CPI appears 8 times, shuffled
+    raw = np.ascontiguousarray(distinct[order])
+    ref = mcode.load_ref("refDDCDataMF1")
+    cfar = synth.cfar_tuple(synth.S3_CFAR)
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, max_det=1 << 20) as ctx:
+        rdm, dets, n = ctx.chain(raw, B)
+    assert n == len(dets) and n > 0
+    picks = np.random.default_rng(65).choice(B, size=4, replace=False)
+    assert len({int(order[i]) for i in picks}) >= 3
+    for i in picks:
+        src = int(order[i])
+        out = vec.chain(distinct[src:src + 1], 1, P, R, C, ("single", ref), cfar, near_tol=RTOL)
+        _close(rdm[i:i + 1], out["rdm"])
+        d = dets[dets["cpi"] == i].copy()
+        d["cpi"] = 0
+        _compare_flags(d, out, 1, C, P, R, lib)
+    # replicas of one distinct CPI agree bit for bit wherever they sit in the batch (chunk / slot boundaries included)
+    for src in range(D):
+        idx = np.flatnonzero(order == src)
+        for j in idx[1:]:
+            assert np.array_equal(rdm[idx[0]], rdm[j])
+
+
+def test_chain_without_rdm_output_matches_across_chunks(lib):
+    """rdm_out = NULL with several chunks in flight on the slot streams: each chunk needs its own RDM scratch (the range
+    stage and the detection amplitudes read it).  Detections must equal those of the run that returns the RDM."""
+    P, R, C, B = 64, 1024, 16, 6
+    raw, _ = synth.s3_batch(B, P=P, R=R, C=C, n_targets=6, r_lo=50, r_hi=R - 100)
+    ref = mcode.load_ref("refDDCDataMF1")
+    cfar = synth.cfar_tuple(synth.S3_CFAR)
+
+    def key(d):
+        return np.sort(d, order=["cpi", "lane", "v", "r", "kind"])
+
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=1, max_det=1 << 20) as ctx:
+        rdm, dets_a, na = ctx.chain(raw, B, want_rdm=True)
+        for _ in range(5):
+            _, dets_b, nb = ctx.chain(raw, B, want_rdm=False)
+            assert na == nb
+            a, b = key(dets_a), key(dets_b)
+            assert all(np.array_equal(a[f], b[f]) for f in a.dtype.names)
 
 
 def test_chain_detection_overflow_is_reported(lib):
@@ -697,9 +760,9 @@ def test_chain_on_dbf24_payloads(lib, P, R, n_ch, B, chunk):
     _compare_flags(dets, out, B, ncol, P, R, lib)
 
 
-def test_chain_S5_full_size_two_lanes_against_oracle(lib):
+def test_chain_S5_full_size_all_lanes_against_oracle(lib):
     """Configuration S5 at BASELINE's full size (256 PRT x 16384 range x 16 lanes, refDBFDataMF1, iSTC + MTI): the oracle
-    is run on two of the sixteen lanes (all range cells) and compared cell by cell; all lanes obey the 0-v mask."""
+    is run lane by lane on all sixteen lanes (all range cells) and compared cell by cell."""
     P, R, C = 256, 16384, 16
     ref = mcode.load_ref("refDBFDataMF1")
     raw, _ = synth.s3_cpi(0, P=P, R=R, C=C, ref=ref, seed0=5000, r_lo=100, r_hi=R - 200, exclude=(-3, -2, -1, 0, 1, 2, 3))
@@ -710,7 +773,7 @@ def test_chain_S5_full_size_two_lanes_against_oracle(lib):
         ctx.set_stc(stc)
         rdm, dets, n = ctx.chain(raw, 1)
     assert np.all(rdm[:, :, 125:130, :] == 0) and n > 0
-    for lane in (0, 15):
+    for lane in range(C):
         sub = np.ascontiguousarray(raw[:, :, :, lane:lane + 1, :])
         out = vec.chain(sub, 1, P, R, 1, ("single", ref), cfar, stc=stc, mti_lag=30, near_tol=RTOL)
         _close(rdm[:, lane:lane + 1], out["rdm"])

@@ -95,6 +95,19 @@ def test_reader_truncated_stream_and_geometry_mismatch(tmp_path):
         FrameReader(tmp_path / "does_not_exist")
 
 
+def test_reader_corrupt_head_does_not_allocate_terabytes(tmp_path):
+    """A PRT head whose pulse_data_num is garbage (0xFFFFFFF0 samples) ends the stream gracefully -- like the short fread of
+    FrameDataRead_xzr.m:122-127 -- instead of asking for a multi-terabyte buffer or letting bad_alloc cross the C ABI."""
+    n_prt, n_range, ch = 2, 20, 16
+    _, blob = _stream(1, n_prt, n_range, ch, seed=7)
+    bad = bytearray(blob)
+    bad[24:28] = (0xFFFFFFF0).to_bytes(4, "little")                      # h[6] = pulse_data_num of the first PRT head
+    _write_capture(tmp_path, bytes(bad), [])
+    rd = FrameReader(tmp_path)
+    _, _, nread, eos = rd.next_frame(n_prt, n_range, ch)
+    assert nread == 0 and eos
+
+
 def test_reader_dbf24_frames_round_trip_and_type_check(tmp_path):
     """DBF-type captures (data_type 2): the reader hands back the padded 24-bit payloads the device decoder takes; asking for
     DDC frames on such a capture is refused."""
