@@ -217,7 +217,10 @@ int rb200_chain_enqueue(rb200_ctx* ctx, const int16_t* raw_dev, int n_cpi, float
 int rb200_chain_fetch(rb200_ctx* ctx, rb200_det* dets_host, int* n_det);
 
 /* Device-side intermediates of the last chain call (parity tests): pulse-compressed samples as
- * float2 [cpi][lane][prt][range] for the last processed chunk.                                    */
+ * float2 [cpi][lane][prt][range] for the last processed chunk.  The default chain for 64 PRT x 16 int16 lanes keeps that
+ * intermediate in shared memory (single-pass kernel: MP/fun_MTD_produce.m:67-79 in one pass); rb200_set_debug_keep_pc(ctx, 1)
+ * selects the pipeline that materialises it in device memory so that it can be fetched.                                 */
+int rb200_set_debug_keep_pc(rb200_ctx* ctx, int on);
 int rb200_debug_fetch_pc(rb200_ctx* ctx, int cpi_in_chunk, float* out_ri);
 
 /* Milliseconds between the first and last kernel of the last chain call (CUDA events).            */

@@ -295,6 +295,10 @@ class Context:
             self._ck(st)
         return dets[: min(n.value, self.cfg.max_det)].copy(), n.value
 
+    def set_debug_keep_pc(self, on=True):
+        """Run later chain calls with the pulse-compressed intermediate in device memory (needed by debug_fetch_pc)."""
+        self._ck(self._lib.rb200_set_debug_keep_pc(self._h, int(bool(on))))
+
     def debug_fetch_pc(self, cpi_in_chunk=0):
         c = self.cfg
         out = np.zeros((self.n_out_lanes, c.n_prt, c.n_range), dtype=np.complex64)

@@ -184,6 +184,9 @@ struct rb200_ctx {
     int dbf_beams = 0;
     DevBuf ring, megactr;          // fused persistent chain: L2-resident PC ring, work / completion counters
     bool last_was_mega = false;
+    bool last_was_onepass = false;
+    bool keep_pc = false;          // rb200_set_debug_keep_pc: run the chain with the pulse-compressed intermediate in HBM
+    int coop_launch = 0;           // cudaDevAttrCooperativeLaunch
     int n_sms = 148;
     // persistent-grid sizing (CTAs per SM): 3/3 fills the SM with one kernel at a time; 2/1 lets the compute-bound PC
     // kernel of chunk i+1 and the HBM-bound MTD kernel of chunk i be co-resident (registers: 2*20.5K + 19.6K <= 64K)
@@ -194,6 +197,7 @@ struct rb200_ctx {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
         DevBuf pc, colmask, vlist, count, raw, rdm, beams;
+        DevBuf op_ring, op_flags;      // single-pass kernel: de-interleaved input ring and team hand-shake flags of this slot
     };
     static const int kMaxSlots = 4;
     Slot slots[kMaxSlots];
@@ -635,6 +639,7 @@ extern "C" int rb200_create(rb200_ctx** out, int device, const rb200_config* cfg
     if (validate_cfar(c, k)) { g_create_error = c->err; delete c; return RB200_ERR_ARG; }
     cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device);
     c->env.read();
+    cudaDeviceGetAttribute(&c->coop_launch, cudaDevAttrCooperativeLaunch, device);
     if (const char* e1 = getenv("RB200_PC_CTAS")) c->pc_ctas_per_sm = atoi(e1);
     if (const char* e2 = getenv("RB200_MTD_CTAS")) c->mtd_ctas_per_sm = atoi(e2);
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -1407,6 +1412,23 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     memset(&m64, 0, sizeof m64);
     int n_slots = 1;
     c->last_was_mega = false;
+    c->last_was_onepass = false;
+    // ---- single-pass kernel (onepass_kernel.cu): P = 64, 16 interleaved int16 lanes, one matched-filter segment covering the
+    //      whole PRT, default velocity windows; the pulse-compressed intermediate stays in shared memory
+    bool onepass = false;
+    int op_V = 0, op_tiles = 0;
+    if (fused && !c->env.no_onepass && !c->keep_pc && c->coop_launch && C == 16 && Cin == 16 && !planar_in && c->gain_n == 0 && c->plan.valid &&
+        c->plan.segs.size() == 1 && c->plan.classes.size() == 1 && c->plan.classes[0].nt == 256 && (R % 4) == 0) {
+        const PcSegDev& d = c->plan.segs[0].d;
+        const bool whole = d.in_start == 0 && d.out_start == 0 && d.in_len == R && d.out_len == R && d.pre == 0 && d.rot == 0 && d.h_off == 0;
+        const int V = onepass_tile_valid(d.n_taps);
+        const bool aligned = (raw_host || (reinterpret_cast<uintptr_t>(raw_dev) & 15) == 0) && (!rdm_dev || (reinterpret_cast<uintptr_t>(rdm_dev) & 15) == 0);
+        if (whole && V >= 64 && d.V >= V && aligned) {
+            onepass = true;
+            op_V = V;
+            op_tiles = (R + V - 1) / V;
+        }
+    }
     // ---- fused persistent kernel for the whole batch (chain64_kernel.cu): device-resident input and output, 16 channels,
     //      one 256-sample tile class covering the whole PRT
     if (fused && raw_dev && rdm_dev && !raw_host && !rdm_host && C == 16 && !planar_in && c->plan.valid && c->plan.classes.size() == 1 &&
@@ -1508,7 +1530,12 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         n_slots = std::min(n_slots, (n_cpi + G - 1) / G);
         for (int i = 0; i < n_slots; ++i) {
             rb200_ctx::Slot& sl = c->slots[i];
-            CK(c, sl.pc.ensure((size_t)G * cpi_cells * sizeof(float2)));
+            if (!onepass) CK(c, sl.pc.ensure((size_t)G * cpi_cells * sizeof(float2)));
+            else {
+                const int teams = onepass_teams(c->n_sms, G * op_tiles);
+                CK(c, sl.op_ring.ensure(onepass_ring_bytes(teams)));
+                CK(c, sl.op_flags.ensure((size_t)teams * 16 * sizeof(int)));
+            }
             CK(c, sl.colmask.ensure((size_t)G * C * R * sizeof(unsigned long long)));
             CK(c, sl.vlist.ensure((size_t)k.max_det * sizeof(rb200_det)));
         }
@@ -1545,6 +1572,47 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         const bool timed = c->stage_timing && c->stage_used + 4 <= 65536;
         if (timed) { stage_event(c, cs); c->stage_cpis.push_back(g); }
         int rc;
+        if (onepass) {
+            OnePassParams op;
+            memset(&op, 0, sizeof op);
+            op.raw = reinterpret_cast<const int*>(raw_chunk);
+            op.rdm = rdm_chunk;
+            op.hperm = c->plan.hperm.as<float2>();
+            op.tw = c->plan.classes[0].tw.as<float2>();
+            op.ring = sl.op_ring.as<int>();
+            op.flags = sl.op_flags.as<int>();
+            op.colmask = sl.colmask.as<unsigned long long>();
+            op.dets = sl.vlist.p;
+            op.det_count = sl.count.as<int>();
+            op.err_flag = c->errflag.as<int>();
+            op.max_det = k.max_det;
+            op.R = R; op.V = op_V; op.n_tiles = op_tiles; op.n_cpi = g;
+            op.n_teams = onepass_teams(c->n_sms, g * op_tiles);
+            op.cpi0 = c0;
+            op.meth_v = k.cfar_method_v;
+            op.tv_over_ref = m64.tv_over_ref;
+            op.keep_mask = 0ull;
+            for (int i = 0; i < 64; ++i) {
+                op.win[i] = m64.win[i];
+                if (m64.keep[i] != 0.f) op.keep_mask |= 1ull << i;
+            }
+            op.segs = c->cfar_segs;
+            CK(c, cudaMemsetAsync(sl.op_flags.p, 0, (size_t)op.n_teams * 16 * sizeof(int), cs));
+            CK(c, launch_onepass(op, cs));
+            c->launches++;
+            if (timed) { stage_event(c, cs); stage_event(c, cs); }      // "pc" = the whole single-pass kernel, "mtd" = 0
+            cp.cpi0 = c0;
+            CK(c, launch_cfar_r64(rdm_chunk, cp, (float)k.cfar_t_r, sl.vlist.p, sl.count.as<int>(), c->dets_v.p, c->dets_2d.p,
+                                  c->counters.as<int>(), sl.colmask.as<unsigned long long>(), R, c->errflag.as<int>(), c->n_sms, cs));
+            c->launches++;
+            if (rdm_host)
+                CK(c, cudaMemcpyAsync(rdm_host + (size_t)c0 * cpi_cells, rdm_chunk, (size_t)g * cpi_cells * sizeof(float), cudaMemcpyDeviceToHost, cs));
+            if (timed) stage_event(c, cs);
+            c->last_chunk_cpis = g;
+            c->last_pc = nullptr;
+            c->last_was_onepass = true;
+            continue;
+        }
         if (dbf24_ch > 0) {
             // f1: 24-bit DBF-type payload -> planar [cpi][beam][prt][range], one launch per CPI of the chunk
             for (int q = 0; q < g; ++q) {
@@ -1685,11 +1753,17 @@ extern "C" int rb200_chain_dbf24(rb200_ctx* c, const uint8_t* payload, int n_ch,
     return chain_fetch(c, dets, dets && is_device_ptr(dets), n_det, st);
 }
 
+extern "C" int rb200_set_debug_keep_pc(rb200_ctx* c, int on) {
+    if (!c) return RB200_ERR_ARG;
+    c->keep_pc = on != 0;
+    return RB200_OK;
+}
+
 extern "C" int rb200_debug_fetch_pc(rb200_ctx* c, int cpi_in_chunk, float* out_ri) {
     if (!c || !out_ri || cpi_in_chunk < 0 || cpi_in_chunk >= c->last_chunk_cpis) return fail(c, RB200_ERR_ARG, "debug_fetch_pc: bad argument");
     cudaSetDevice(c->device);
     const size_t cpi_cells = (size_t)c->cfg.n_prt * c->cfg.n_range * (c->dbf_beams ? c->dbf_beams : c->cfg.n_lanes);
-    if (!c->last_pc) return fail(c, RB200_ERR_ARG, "debug_fetch_pc: no chunked chain call yet (set RB200_NO_MEGA=1 to keep the intermediate)");
+    if (!c->last_pc) return fail(c, RB200_ERR_ARG, "debug_fetch_pc: the last chain call kept its intermediate on chip (call rb200_set_debug_keep_pc(ctx, 1) first)");
     CK(c, cudaDeviceSynchronize());
     CK(c, cudaMemcpy(out_ri, c->last_pc + (size_t)cpi_in_chunk * cpi_cells, cpi_cells * sizeof(float2), cudaMemcpyDeviceToHost));
     return RB200_OK;

@@ -136,5 +136,25 @@ struct Chain64Params {
     int* err_flag;
 };
 
+// single-pass chain for P = 64, 16 interleaved lanes (onepass_kernel.cu)
+struct OnePassParams {
+    const int* raw;                 // wire int16 pairs [cpi][prt][range][16 lanes] of this launch (16-byte aligned)
+    float* rdm;                     // [cpi][lane][v][range] of this launch (16-byte aligned)
+    const float2* hperm;            // reference spectrum of the single MF segment, position q*16 + k <-> bin q + 16*k, times scale/256
+    const float2* tw;               // tw[k*16 + u] = exp(-2*pi*i*u*k/256)
+    int* ring;                      // de-interleaved input ring: [team][4 slots][16 lanes][64 prt][272] words
+    int* flags;                     // [team][16]: rounds produced by each member (zeroed before the launch)
+    unsigned long long* colmask;    // [cpi*16 + lane][R]: bit v = velocity hit at (v, r)
+    void* dets;                     // rb200_det list of velocity hits (per-slot scratch list)
+    int* det_count;
+    int* err_flag;
+    int max_det;
+    int R, V, n_tiles, n_cpi, n_teams, cpi0;
+    int meth_v;
+    float tv_over_ref;
+    unsigned long long keep_mask;   // bit row = 0 for zero-velocity rows
+    float win[64];                  // Kaiser window
+    CfarSegs segs;
+};
 
 }  // namespace rb

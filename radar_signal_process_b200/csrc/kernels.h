@@ -40,6 +40,13 @@ cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, co
 // ---- fused persistent PC + MTD64 + velocity CFAR for a whole batch (chain64_kernel.cu)
 cudaError_t launch_chain64(const Chain64Params& q, int n_sms, cudaStream_t st);
 
+// ---- single-pass chain for P = 64, 16 lanes: unpack + PC + MTD + 0-v + velocity CFAR with the PC intermediate in shared memory
+// (onepass_kernel.cu)
+int onepass_tile_valid(int n_taps);                 // V: valid lags per 256-sample tile (multiple of 4, <= 192)
+int onepass_teams(int n_sms, int n_tile_groups);    // teams of 16 CTAs
+size_t onepass_ring_bytes(int n_teams);
+cudaError_t launch_onepass(const OnePassParams& p, cudaStream_t st);
+
 // ---- K3 CFAR (cfar_kernels.cu)
 // chain variant: float RDM [slab][V][R] row-major -> velocity-hit list + 2-D list (+ optional dense uint8 flags)
 cudaError_t launch_cfar_f32(const float* rdm, const CfarParams& p, float t_r, float t_v, int n_slabs, void* dets_v, int* count_v,

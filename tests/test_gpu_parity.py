@@ -280,9 +280,15 @@ def test_chain_S3_two_cpis(lib):
     cfar = synth.cfar_tuple(synth.S3_CFAR)
     out = vec.chain(raw, B, P, R, C, ("single", ref), cfar, near_tol=RTOL)
     with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=B) as ctx:
-        rdm, dets, n = ctx.chain(raw, B)
+        rdm, dets, n = ctx.chain(raw, B)                      # default: single-pass kernel, intermediate stays on chip
+        assert ctx.last_launch_count() >= 2 and ctx.last_device_ms() > 0
+        ctx.set_debug_keep_pc(True)                           # the pipeline with the intermediate in device memory
+        rdm_k, dets_k, n_k = ctx.chain(raw, B)
         pc = ctx.debug_fetch_pc(B - 1)
-        assert ctx.last_launch_count() >= 3 and ctx.last_device_ms() > 0
+        assert ctx.last_launch_count() >= 3
+    print("S3 RDM rel err (HBM-intermediate pipeline) %.2e" % _close(rdm_k, out["rdm"]))
+    _compare_flags(dets_k, out, B, C, P, R, lib)
+    print("S3 single-pass vs HBM-intermediate RDM rel diff %.2e" % _close(rdm, rdm_k, tol=1e-5))
     print("S3 PC rel err %.2e" % _close(pc, out["pc"][B - 1]))
     print("S3 RDM rel err %.2e" % _close(rdm, out["rdm"]))
     assert n == len(dets) and n > 0
@@ -360,6 +366,7 @@ def test_chain_full_size_properties(lib):
     imp = np.zeros((1, P, R, C, 2), dtype=np.int16)
     imp[0, :, 1000, :, 0] = 1
     with _chain_ctx(lib, P, R, C, 1, lib.waveforms.segments_single(R, ref), cfar) as ctx:
+        ctx.set_debug_keep_pc(True)
         ctx.chain(imp, 1, want_rdm=False, allow_overflow=True)   # all-zero background: 0 >= 0 flags everything
         pc = ctx.debug_fetch_pc(0)
     want = np.zeros(R, dtype=complex)
