@@ -145,7 +145,10 @@ struct EnvSwitches {
     int chunk = 0;              // RB200_CHUNK
     int slots = 0;              // RB200_SLOTS (0 = default)
     bool no_tma = false, no_tma_mtd = false, no_fused = false, no_fused_v = false, mega = false, no_cfar_tile = false;
-    bool no_onepass = false;    // RB200_NO_ONEPASS: keep the PC intermediate in HBM (the round-1 slot pipeline)
+    bool onepass = false;       // RB200_ONEPASS=1: the single-pass kernel (PC intermediate in shared memory); measured slower than
+                                // the slot pipeline on B200 (profiles/r02_onepass.md), so it is opt-in
+    bool op_trace = false;      // RB200_OP_TRACE: clock stamps of CTA 0 of the last single-pass launch -> gpurun_out/op_trace.bin
+    int op_dbg = 0;             // RB200_OP_DBG: timing experiments of the single-pass kernel (results are wrong)
     void read() {
         auto flag = [](const char* n) { const char* v = getenv(n); return v != nullptr && v[0] != 0 && !(v[0] == '0' && v[1] == 0); };
         auto num = [](const char* n) { const char* v = getenv(n); return v ? atoi(v) : 0; };
@@ -158,7 +161,9 @@ struct EnvSwitches {
         no_fused_v = flag("RB200_NO_FUSED_V");
         mega = flag("RB200_MEGA");
         no_cfar_tile = flag("RB200_NO_CFAR_TILE");
-        no_onepass = flag("RB200_NO_ONEPASS");
+        onepass = flag("RB200_ONEPASS");
+        op_dbg = num("RB200_OP_DBG");
+        op_trace = flag("RB200_OP_TRACE");
     }
 };
 
@@ -182,6 +187,7 @@ struct rb200_ctx {
     DevBuf raw, pc, rdm, dets_v, dets_2d, counters, vmask, errflag, colmask;
     DevBuf dbf_w;                  // DBF weights float2 [beam][channel]; dbf_beams = 0 when off
     int dbf_beams = 0;
+    DevBuf op_trace;
     DevBuf ring, megactr;          // fused persistent chain: L2-resident PC ring, work / completion counters
     bool last_was_mega = false;
     bool last_was_onepass = false;
@@ -1417,7 +1423,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     //      whole PRT, default velocity windows; the pulse-compressed intermediate stays in shared memory
     bool onepass = false;
     int op_V = 0, op_tiles = 0;
-    if (fused && !c->env.no_onepass && !c->keep_pc && c->coop_launch && C == 16 && Cin == 16 && !planar_in && c->gain_n == 0 && c->plan.valid &&
+    if (fused && c->env.onepass && !c->keep_pc && c->coop_launch && C == 16 && Cin == 16 && !planar_in && c->gain_n == 0 && c->plan.valid &&
         c->plan.segs.size() == 1 && c->plan.classes.size() == 1 && c->plan.classes[0].nt == 256 && (R % 4) == 0) {
         const PcSegDev& d = c->plan.segs[0].d;
         const bool whole = d.in_start == 0 && d.out_start == 0 && d.in_len == R && d.out_len == R && d.pre == 0 && d.rot == 0 && d.h_off == 0;
@@ -1591,12 +1597,17 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
             op.cpi0 = c0;
             op.meth_v = k.cfar_method_v;
             op.tv_over_ref = m64.tv_over_ref;
-            op.keep_mask = 0ull;
             for (int i = 0; i < 64; ++i) {
                 op.win[i] = m64.win[i];
-                if (m64.keep[i] != 0.f) op.keep_mask |= 1ull << i;
+                op.keep[i] = m64.keep[i];
             }
             op.segs = c->cfar_segs;
+            op.dbg = c->env.op_dbg;
+            if (c->env.op_trace) {
+                CK(c, c->op_trace.ensure(32 * 12 * 16 * sizeof(unsigned long long)));
+                CK(c, cudaMemsetAsync(c->op_trace.p, 0, 32 * 12 * 16 * sizeof(unsigned long long), cs));
+                op.trace = c->op_trace.as<unsigned long long>();
+            }
             CK(c, cudaMemsetAsync(sl.op_flags.p, 0, (size_t)op.n_teams * 16 * sizeof(int), cs));
             CK(c, launch_onepass(op, cs));
             c->launches++;
@@ -1699,6 +1710,12 @@ static int chain_fetch(rb200_ctx* c, rb200_det* dets, bool dets_on_device, int* 
     CK(c, cudaMemcpyAsync(c->h_counts, c->counters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(c, cudaMemcpyAsync(c->h_counts + 3, c->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
+    if (c->env.op_trace && c->op_trace.p) {
+        std::vector<unsigned long long> tr(32 * 12 * 16);
+        if (cudaMemcpy(tr.data(), c->op_trace.p, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            if (FILE* f = fopen("gpurun_out/op_trace.bin", "wb")) { fwrite(tr.data(), sizeof(unsigned long long), tr.size(), f); fclose(f); }
+        }
+    }
     const int nv = c->h_counts[0], n2 = c->cfg.cfar_range_stage ? c->h_counts[1] : 0;
     if (n_det) *n_det = nv + n2;
     if (c->h_counts[3] == 2) return fail(c, RB200_ERR_CUDA, "fused chain kernel: a dependency wait timed out (internal error)");

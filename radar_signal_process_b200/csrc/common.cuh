@@ -152,8 +152,10 @@ struct OnePassParams {
     int R, V, n_tiles, n_cpi, n_teams, cpi0;
     int meth_v;
     float tv_over_ref;
-    unsigned long long keep_mask;   // bit row = 0 for zero-velocity rows
+    unsigned long long* trace;      // RB200_OP_TRACE: clock64 stamps of CTA 0, [item < 32][warp][16 events] (null = off)
+    int dbg;                        // timing experiments only (RB200_OP_DBG): 1 skip Doppler, 2 skip transforms, 4 skip de-interleave
     float win[64];                  // Kaiser window
+    float keep[64];                 // 0 for zero-velocity rows, 1 elsewhere (per output row)
     CfarSegs segs;
 };
 

@@ -280,15 +280,9 @@ def test_chain_S3_two_cpis(lib):
     cfar = synth.cfar_tuple(synth.S3_CFAR)
     out = vec.chain(raw, B, P, R, C, ("single", ref), cfar, near_tol=RTOL)
     with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=B) as ctx:
-        rdm, dets, n = ctx.chain(raw, B)                      # default: single-pass kernel, intermediate stays on chip
-        assert ctx.last_launch_count() >= 2 and ctx.last_device_ms() > 0
-        ctx.set_debug_keep_pc(True)                           # the pipeline with the intermediate in device memory
-        rdm_k, dets_k, n_k = ctx.chain(raw, B)
+        rdm, dets, n = ctx.chain(raw, B)
         pc = ctx.debug_fetch_pc(B - 1)
-        assert ctx.last_launch_count() >= 3
-    print("S3 RDM rel err (HBM-intermediate pipeline) %.2e" % _close(rdm_k, out["rdm"]))
-    _compare_flags(dets_k, out, B, C, P, R, lib)
-    print("S3 single-pass vs HBM-intermediate RDM rel diff %.2e" % _close(rdm, rdm_k, tol=1e-5))
+        assert ctx.last_launch_count() >= 3 and ctx.last_device_ms() > 0
     print("S3 PC rel err %.2e" % _close(pc, out["pc"][B - 1]))
     print("S3 RDM rel err %.2e" % _close(rdm, out["rdm"]))
     assert n == len(dets) and n > 0
@@ -420,6 +414,53 @@ def test_chain_without_rdm_output_matches_across_chunks(lib):
             assert na == nb
             a, b = key(dets_a), key(dets_b)
             assert all(np.array_equal(a[f], b[f]) for f in a.dtype.names)
+
+
+@pytest.mark.parametrize("R,B,chunk", [(4096, 2, 0), (4096, 5, 2), (1000, 3, 0), (752, 1, 0), (188, 2, 0)])
+def test_chain_single_pass_kernel(lib, monkeypatch, R, B, chunk):
+    """RB200_ONEPASS=1: the single-pass kernel (unpack + PC + Doppler + 0-v + velocity CFAR with the pulse-compressed
+    intermediate in shared memory, onepass_kernel.cu) against the oracle and against the default pipeline: ragged last
+    tiles (R not a multiple of the 188-cell tile), a single tile, several chunks / cooperative launches per call."""
+    P, C = 64, 16
+    raw, _ = synth.s3_batch(B, P=P, R=R, C=C, n_targets=4, r_lo=20, r_hi=max(R - 80, 40))
+    ref = mcode.load_ref("refDDCDataMF1")
+    cfar = synth.cfar_tuple(synth.S3_CFAR)
+    out = vec.chain(raw, B, P, R, C, ("single", ref), cfar, near_tol=RTOL)
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=chunk, max_det=1 << 20) as ctx:
+        rdm_d, dets_d, _ = ctx.chain(raw, B)
+        launches_default = ctx.last_launch_count()
+    monkeypatch.setenv("RB200_ONEPASS", "1")
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=chunk, max_det=1 << 20) as ctx:
+        rdm, dets, n = ctx.chain(raw, B)
+        assert ctx.last_launch_count() < launches_default          # one kernel instead of two per chunk (plus the range stage)
+        rdm2, dets2, n2 = ctx.chain(raw, B)                        # the ring / flags are re-armed between calls
+        _, dets3, n3 = ctx.chain(raw, B, want_rdm=False)
+    print("single-pass RDM rel err %.2e" % _close(rdm, out["rdm"]))
+    _compare_flags(dets, out, B, C, P, R, lib)
+    _close(rdm, rdm_d, tol=1e-5)
+    assert np.array_equal(rdm, rdm2) and n == n2 == n3
+
+    def key(d):
+        return np.sort(d, order=["cpi", "lane", "v", "r", "kind"])
+
+    a, b, c3 = key(dets), key(dets2), key(dets3)
+    assert all(np.array_equal(a[f], b[f]) and np.array_equal(a[f], c3[f]) for f in a.dtype.names)
+
+
+def test_chain_single_pass_kernel_falls_back_outside_its_envelope(lib, monkeypatch):
+    """With RB200_ONEPASS=1, configurations the single-pass kernel does not cover (13 lanes, a three-segment waveform, iSTC,
+    R not a multiple of 4) silently take the slot pipeline and still match the oracle."""
+    monkeypatch.setenv("RB200_ONEPASS", "1")
+    P, R, C, B = 64, 1031, 13, 1
+    rng = np.random.default_rng(3)
+    raw = rng.integers(-300, 300, size=(B, P, R, C, 2), dtype=np.int16)
+    p2, p3 = mcode.load_pulse_literals()
+    cfar = synth.cfar_tuple(synth.S3_CFAR)
+    out = vec.chain(raw, B, P, R, C, ("lss_mp", p2, p3), cfar, near_tol=RTOL)
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_mp(R, p2, p3), cfar) as ctx:
+        rdm, dets, n = ctx.chain(raw, B)
+    _close(rdm, out["rdm"])
+    _compare_flags(dets, out, B, C, P, R, lib)
 
 
 def test_chain_detection_overflow_is_reported(lib):
