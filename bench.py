@@ -29,12 +29,59 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-P, R, C = 64, 4096, 16
+# Workloads.  S3 is the BASELINE.json headline (configs[2]/[3]); S5 is configs[4]; S1 (configs[0]
+# stand-in) goes through the MATLAB-layout entry points and has its own arm below.
+WORKLOADS = {
+    "S3": dict(P=64, R=4096, C=16, ref="REF_DDC", cfar=(5, 7, 5.0, 0, 5, 7, 5.0, 0, 0, 1), mti=0, stc=False, cpis=64, distinct=8,
+               synth=dict(seed0=1234, r_lo=100, r_hi=3900, exclude=(-1, 0)),
+               name="S3 synthetic LFM DDC 4096 range x 64 PRT x 16 lanes, plan single (refDDCDataMF1), CFAR 5/7/T5/GO",
+               metric="CPI frames/s (PC->MTD->0v->CFAR, 64 PRT x 4096 range x 16 lanes int16 DDC)",
+               kernel="pc_fft_tma_kernel (K1: int16 unpack + overlap-save pulse compression; the largest share of the chain's device time)",
+               ncu_regex="pc_fft_tma"),
+    "S5": dict(P=256, R=16384, C=16, ref="REF_DBF", cfar=(5, 7, 7.0, 0, 5, 7, 7.0, 0, 0, 1), mti=30, stc=True, cpis=4, distinct=1,
+               synth=dict(seed0=5000, r_lo=100, r_hi=16384 - 200, exclude=(-3, -2, -1, 0, 1, 2, 3)),
+               name="S5 DBF mode 16384 range x 256 PRT x 16 lanes, refDBFDataMF1, iSTC + MTI(30), CFAR 5/7/T7/GO",
+               metric="CPI frames/s (iSTC->PC->MTI->MTD->0v->CFAR, 256 PRT x 16384 range x 16 lanes int16)",
+               kernel="pc_fft_tma_kernel (K1: int16 unpack + iSTC + overlap-save pulse compression)",
+               ncu_regex="pc_fft_tma"),
+}
+W = dict(WORKLOADS["S3"])                 # the active workload (set in main)
+P, R, C = W["P"], W["R"], W["C"]
 CELLS = P * R * C
 ALG_BYTES_PER_CPI = CELLS * 8          # 4 B int16 I/Q read + 4 B fp32 RDM magnitude written per cell
-CFAR = (5, 7, 5.0, 0, 5, 7, 5.0, 0, 0, 1)
-K1_DRAM_BYTES_PER_CPI = (134.590208e6 + 215.659008e6) / 8.0     # ncu, cold cache, see profiles/r01j_ncu_full_final.txt
-METRIC = "CPI frames/s (PC->MTD->0v->CFAR, 64 PRT x 4096 range x 16 lanes int16 DDC)"
+CFAR = W["cfar"]
+METRIC = W["metric"]
+
+
+def select_workload(name):
+    global W, P, R, C, CELLS, ALG_BYTES_PER_CPI, CFAR, METRIC
+    W = dict(WORKLOADS[name])
+    P, R, C = W["P"], W["R"], W["C"]
+    CELLS = P * R * C
+    ALG_BYTES_PER_CPI = CELLS * 8
+    CFAR = W["cfar"]
+    METRIC = W["metric"]
+
+
+def s5_stc_curve():
+    return 30.0 * (1.0 - np.arange(1025) / 1024.0)      # linear 30 -> 0 dB over the first 1025 cells (MP/fun_iSTC.m:6-9)
+
+
+def synth(n, first_cpi=0, distinct=None):
+    from radar_signal_process_b200 import waveforms, workload
+    return workload.synth_batch(n, first_cpi=first_cpi, distinct=distinct, P=P, R=R, C=C, ref=getattr(waveforms, W["ref"]), **W["synth"])
+
+
+def oracle_chain(raw, n, lanes=None, near=False):
+    """The checker / CPU baseline: oracle/vec.py on ``n`` CPIs (optionally a subset of lanes); ``near`` adds the
+    near-threshold masks the parity check needs (not part of the timed reference path)."""
+    from oracle import vec
+    from radar_signal_process_b200 import waveforms
+    if lanes is not None:
+        raw = np.ascontiguousarray(raw[:, :, :, lanes, :])
+    nl = raw.shape[3]
+    return vec.chain(raw, n, P, R, nl, ("single", getattr(waveforms, W["ref"])), CFAR, stc=s5_stc_curve() if W["stc"] else None,
+                     mti_lag=W["mti"], near_tol=1e-4 if near else None)
 
 
 def measured_peak():
@@ -140,17 +187,23 @@ class NvmlSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------------
 def cpu_reference_rate(n_cpis, first_cpi=0, workers=None):
     """Time the oracle port of the reference chain (vectorised NumPy/SciPy double precision, all host
-    threads for the FFTs) on ``n_cpis`` CPIs of the benchmark workload.  Returns (cpis_per_s, seconds)."""
+    threads for the FFTs) on a bounded sample of the benchmark workload.  Returns (cpis_per_s, seconds, sample text)."""
     from oracle import vec                                   # the checker, executed here only as the CPU baseline
-    from radar_signal_process_b200 import waveforms, workload
     if workers:
         vec.set_workers(workers)
-    raw = workload.synth_batch(n_cpis, first_cpi=first_cpi)
+    if P * R * C > 2 ** 24:                                  # S5: one CPI is 67 M cells -- time 2 of its 16 lanes
+        raw = synth(1, first_cpi=first_cpi)
+        lanes = [0, C - 1]
+        t0 = time.perf_counter()
+        oracle_chain(raw, 1, lanes=lanes)
+        dt = time.perf_counter() - t0
+        return len(lanes) / C / dt, dt, "%d of %d lanes of one CPI through oracle/vec.py (float64, scipy.fft workers=all), %.1f s, scaled" % (len(lanes), C, dt)
+    raw = synth(n_cpis, first_cpi=first_cpi)
     t0 = time.perf_counter()
     for i in range(n_cpis):
-        vec.chain(raw[i:i + 1], 1, P, R, C, ("single", waveforms.REF_DDC), CFAR)
+        oracle_chain(raw[i:i + 1], 1)
     dt = time.perf_counter() - t0
-    return n_cpis / dt, dt
+    return n_cpis / dt, dt, "%d CPIs of the workload through oracle/vec.py (float64, scipy.fft workers=all), %.1f s" % (n_cpis, dt)
 
 
 def cpu_loop_faithful_rate():
@@ -159,7 +212,7 @@ def cpu_loop_faithful_rate():
     S3 CPI, extrapolated x16 lanes.  Returns (cpis_per_s, seconds measured)."""
     from oracle import mcode
     from radar_signal_process_b200 import waveforms, workload
-    raw = workload.synth_batch(1)
+    raw = synth(1)
     x = raw[0, :, :, 0, 0].astype(np.float64) + 1j * raw[0, :, :, 0, 1].astype(np.float64)      # lane 0: P x R
     t0 = time.perf_counter()
     pc = np.zeros(x.shape, dtype=np.complex128)
@@ -179,14 +232,16 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = max(1, args.ref_cpis)
-    from oracle import vec
-    from radar_signal_process_b200 import waveforms, workload
-    raw = workload.synth_batch(sample)
+    if args.workload == "S1":
+        return run_s1_reference(args)
+    big = P * R * C > 2 ** 24
+    sample = 1 if big else max(1, args.ref_cpis)
+    lanes = [0] if big else None                             # S5: one lane of one CPI per step, scaled by the lane count
+    raw = synth(sample)
 
     def step():
         for i in range(sample):
-            vec.chain(raw[i:i + 1], 1, P, R, C, ("single", waveforms.REF_DDC), CFAR)
+            oracle_chain(raw[i:i + 1], 1, lanes=lanes)
 
     for _ in range(args.warmup):
         step()
@@ -194,18 +249,110 @@ def run_reference(args):
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
+    value = sample * args.steps / dt * ((len(lanes) / C) if lanes else 1.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "CPI/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "S3 synthetic LFM DDC 4096 range x 64 PRT x 16 lanes, plan single (refDDCDataMF1), CFAR 5/7/T5/GO",
-                   "cpis_per_step": sample, "impl_note": "oracle port of the M-code (vectorised NumPy/SciPy, float64); MATLAB/Octave absent"},
+        "config": {"workload": W["name"], "cpis_per_step": sample,
+                   "impl_note": "oracle port of the M-code (vectorised NumPy/SciPy, float64); MATLAB/Octave absent" +
+                                ("; one of %d lanes per step, value scaled by 1/%d" % (C, C) if lanes else "")},
         "cpu_baseline": {"value": value, "unit": "CPI/s", "cores": cores, "kind": "port",
-                         "sample": "%d CPIs per step x %d steps of the S3 workload" % (sample, args.steps)},
+                         "sample": "%d CPI(s)%s per step x %d steps of the workload" % (sample, " (1 lane)" if lanes else "", args.steps)},
         "e2e": {"value": value, "unit": "CPI/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    print(json.dumps(line))
+
+
+# ---- configuration 1 stand-in (S1): one 1536 x 1031 frame per beam through the MATLAB-layout entry points ----------------
+S1_NAME = "S1 frame 1536 PRT x 1031 range, fun_MTD_produce (segments 82/242/707) + crop 691:845 + 0-v/20 + fun_CFARflag (3 x executeCFAR)"
+S1_METRIC = "frames/s (fun_MTD_produce + main_cfar.m crop/0-v/fun_CFARflag, 1536 PRT x 1031 range, host doubles in and out)"
+
+
+def s1_frame(seed):
+    rng = np.random.default_rng(seed)
+    return np.rint(rng.normal(0, 200, (1536, 1031))) + 1j * np.rint(rng.normal(0, 200, (1536, 1031)))
+
+
+def s1_chain(mod_produce, mod_zero_v, mod_cfar, echo):
+    mtd = mod_produce(echo)                                           # MP/main_produce_dataset_win_xzr.m:37-38
+    crop = mod_zero_v(np.abs(mtd[690:845, :]), 20)                    # CW/main_cfar.m rows 691:845, CW/fun_0v_pressing.m
+    flags = np.zeros_like(crop)
+    for c0, c1 in ((0, 82), (82, 318), (318, 868)):                   # fun_CFARflag, CW/main_cfar.m:142-161
+        f, _ = mod_cfar(crop[:, c0:c1], 5, 7, 5.0, 0, 5, 7, 5.0, 0, 10, 1)
+        flags[:, c0:c1] = f
+    return mtd, flags
+
+
+def run_s1_reference(args):
+    from oracle import mcode, vec
+    p2, p3 = mcode.load_pulse_literals()
+    echo = s1_frame(1)
+
+    def produce(e):
+        return vec.zero_v(vec.process_mtd(vec.lss_pc_mp(e, p2, p3), axis=0), 150, axis=0)
+
+    def cfar(x, *a):
+        return vec.execute_cfar(x, *a)[:2]
+
+    def step():
+        s1_chain(produce, lambda m, d: vec.zero_v(m, d, axis=0), cfar, echo)
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    n = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = time.perf_counter() - t0
+    value = n / dt
+    print(json.dumps({"impl": "reference", "metric": S1_METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": n,
+                      "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": S1_NAME},
+                      "cpu_baseline": {"value": value, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                       "sample": "%d frames through oracle/vec.py" % n},
+                      "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def run_s1(args):
+    """S1 on the GPU: the reference-facing host API (same call sequence as main_produce_dataset_win_xzr.m + main_cfar.m).
+    Inputs and outputs are MATLAB doubles on the host, so every figure here is end to end; `value` repeats it."""
+    import torch
+    import radar_signal_process_b200 as rsp
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    echo = s1_frame(1)
+    for _ in range(max(args.warmup, 3)):
+        mtd, flags = s1_chain(rsp.fun_MTD_produce, rsp.fun_0v_pressing, rsp.executeCFAR, echo)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mtd, flags = s1_chain(rsp.fun_MTD_produce, rsp.fun_0v_pressing, rsp.executeCFAR, echo)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    peak, peak_src = measured_peak()
+    alg = 1536 * 1031 * (16 + 8)                  # complex double in, double out per range-Doppler cell of fun_MTD_produce
+    line = {"metric": S1_METRIC, "value": value, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": S1_NAME, "note": "host-double API: value == e2e (no device-resident form of this entry point)"},
+            "roofline": {"bound": "hbm", "kernel": "whole fun_MTD_produce call (PCIe + layout conversion + pc_fft + mtd_generic)", "achieved": value * alg / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": value * alg / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 1536 * 1031 * 16 + 155 * 868 * 8 * 4,
+                    "d2h_bytes_per_step": 1536 * 1031 * 8 + 155 * 868 * 8 * 7},
+            "gpu_launches": None, "detections_per_step": int(flags.sum())}
+    if not args.no_cpu_baseline:
+        from oracle import mcode, vec
+        p2, p3 = mcode.load_pulse_literals()
+        t0 = time.perf_counter()
+        want = vec.zero_v(vec.process_mtd(vec.lss_pc_mp(echo, p2, p3), axis=0), 150, axis=0)
+        s1_chain(lambda e: want, lambda m, d: vec.zero_v(m, d, axis=0), lambda x, *a: vec.execute_cfar(x, *a)[:2], echo)
+        dtc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 1.0 / dtc, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "one frame through oracle/vec.py (float64), %.1f s" % dtc}
+        line["parity"] = {"rdm_rel_err": float(np.abs(mtd - want).max() / np.abs(want).max())}
     print(json.dumps(line))
 
 
@@ -228,12 +375,45 @@ def bind_to_gpu_numa_node(torch_device):
         return "unbound (%s)" % type(e).__name__
 
 
+def ncu_dram_bytes(regex, workload, cpis):
+    """--ncu: DRAM bytes per launch of the dominant kernel, measured NOW by a short profiled sub-run of this very script
+    (dram__bytes_read.sum + dram__bytes_write.sum, cold cache, averaged over the captured launches)."""
+    import csv
+    import shutil
+    if not shutil.which("ncu"):
+        return None, "ncu not found"
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:" + regex, "-s", "2", "-c", "4",
+           "--csv", sys.executable, os.path.abspath(__file__), "--workload", workload, "--cpis", str(cpis), "--steps", "1", "--warmup", "1",
+           "--no-cpu-baseline", "--e2e-steps", "0", "--no-parity"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600).stdout
+    except Exception as e:
+        return None, "ncu failed: %s" % type(e).__name__
+    rows = [r for r in csv.reader(out.splitlines()) if len(r) > 10]
+    if not rows:
+        return None, "ncu produced no rows"
+    hdr = rows[0]
+    try:
+        i_name, i_val, i_unit, i_id = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("ID")
+    except ValueError:
+        return None, "unexpected ncu csv"
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per_launch = {}
+    for r in rows[1:]:
+        if r[i_name].startswith("dram__bytes"):
+            per_launch.setdefault(r[i_id], 0.0)
+            per_launch[r[i_id]] += float(r[i_val].replace(",", "")) * scale.get(r[i_unit], 1.0)
+    if not per_launch:
+        return None, "no dram metrics in the ncu output"
+    return sum(per_launch.values()) / len(per_launch), "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:%s, %d launches, this run" % (regex, len(per_launch))
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     import radar_signal_process_b200 as rsp
     from radar_signal_process_b200 import distributed as rdist
-    from radar_signal_process_b200 import waveforms, workload
+    from radar_signal_process_b200 import waveforms
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -247,17 +427,29 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.cpis
-    # rank r owns global CPIs [r*B, (r+1)*B)  (weak scaling: per-GPU work fixed)
-    raw_np = workload.synth_batch(B, first_cpi=rank * B, distinct=min(args.distinct, B))
+    cpis = args.cpis if args.cpis > 0 else W["cpis"]
+    distinct = args.distinct if args.distinct > 0 else W["distinct"]
+    if args.scaling == "strong":
+        # one fixed batch of --cpis CPIs block-partitioned over the ranks
+        lo, hi = rdist.shard_range(cpis, rank, world)
+        B, first = hi - lo, lo
+        total_per_step = cpis
+    else:
+        # rank r owns global CPIs [r*B, (r+1)*B)  (weak scaling: per-GPU work fixed)
+        B, first = cpis, rank * cpis
+        total_per_step = world * cpis
+    assert B >= 1, "strong scaling: fewer CPIs than ranks"
+    raw_np = synth(B, first_cpi=first, distinct=min(distinct, B))
     raw_pin = torch.from_numpy(raw_np).pin_memory()
     raw_dev = raw_pin.to(dev, non_blocking=False)
     rdm_dev = torch.empty((B, C, P, R), dtype=torch.float32, device=dev)
     rdm_pin = torch.empty((B, C, P, R), dtype=torch.float32).pin_memory()
 
-    ctx = rsp.Context(local_rank, n_prt=P, n_range=R, n_lanes=C, max_cpi=B, max_det=args.max_det, chunk_cpi=args.chunk)
-    ctx.set_waveform(waveforms.segments_single(R, waveforms.REF_DDC))
+    ctx = rsp.Context(local_rank, n_prt=P, n_range=R, n_lanes=C, max_cpi=B, max_det=args.max_det, chunk_cpi=args.chunk, mti_lag=W["mti"])
+    ctx.set_waveform(waveforms.segments_single(R, getattr(waveforms, W["ref"])))
     ctx.set_cfar(*CFAR)
+    if W["stc"]:
+        ctx.set_stc(s5_stc_curve())
     # a non-default torch stream: its handle goes to the C ABI, so the library's kernels and torch's
     # CUDA events are on the same stream
     stream = torch.cuda.Stream(dev)
@@ -296,12 +488,46 @@ def run_gpu(args):
         step_device()
     e1.record(stream)
     barrier()
+    ms = e0.elapsed_time(e1)
+    # the same step repeated for at least --sustain seconds: a sustained figure next to the K-step one (same clocks record)
+    sustained = None
+    if args.sustain > 0 and ms > 0:
+        reps = max(1, int(np.ceil(args.sustain * 1e3 / ms)))
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        u0.record(stream)
+        for _ in range(reps * args.steps):
+            step_device()
+        u1.record(stream)
+        barrier()
+        sus_ms = u0.elapsed_time(u1)
+        sustained = (reps * args.steps, sus_ms)
     if nvml:
         nvml.active.clear()
         nvml.stop()
-    ms = e0.elapsed_time(e1)
     launches_per_step = ctx.last_launch_count()
     dets, n_det = ctx.chain_fetch(allow_overflow=True)
+
+    # ---- parity of the step just timed: CPI 0 of this rank's batch against the oracle (the checker) ---------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        lanes = [0] if P * R * C > 2 ** 24 else None                    # S5: one lane of the CPI (67 M cells per CPI otherwise)
+        out = oracle_chain(raw_np[0:1], 1, lanes=lanes, near=True)
+        got = rdm_dev[0].cpu().numpy()
+        if lanes is not None:
+            got = got[lanes]
+        want = out["rdm"][0]
+        flag, flagv = rsp.dets_to_flags(dets[dets["cpi"] == 0], 1, C, P, R)
+        if lanes is not None:
+            flag, flagv = flag[:, lanes], flagv[:, lanes]
+        d2 = flag[0] != out["flag"][0]
+        dv = flagv[0] != out["flagV"][0]
+        parity = {"cpi": 0, "lanes": "all" if lanes is None else lanes, "rdm_rel_err": float(np.abs(got - want).max() / np.abs(want).max()),
+                  "rdm_tol": 1e-4, "flags_2d": int(out["flag"][0].sum()), "flags_differ": int(d2.sum()),
+                  "flags_differ_unexcused": int((d2 & ~out["near"][0]).sum()), "flags_v_differ": int(dv.sum()),
+                  "flags_v_differ_unexcused": int((dv & ~out["nearV"][0]).sum()), "near_count": int(out["near"][0].sum()),
+                  "cells": int(want.size), "checker": "oracle/vec.py (float64), near-threshold tolerance 1e-4"}
+
     # per-kernel durations for the roofline object: the same K steps again with CUDA events around every
     # stage of every chunk (chunks serialised on one stream; the headline `value` above is measured without
     # these events and with chunk pipelining on)
@@ -319,87 +545,118 @@ def run_gpu(args):
 
     # ---- end-to-end through the C ABI with pinned host buffers ------------------------------------
     dets_pin = torch.empty(args.max_det * 16, dtype=torch.uint8).pin_memory()
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = max(0, min(args.steps, args.e2e_steps))
+    e2e_s, e2e_do_s, n_e2e = None, None, 0
 
-    def step_e2e():
-        st, n = ctx.chain_ptr(raw_pin.data_ptr(), B, rdm_pin.data_ptr(), dets_pin.data_ptr(), sptr)
+    def step_e2e(with_rdm=True):
+        st, n = ctx.chain_ptr(raw_pin.data_ptr(), B, rdm_pin.data_ptr() if with_rdm else None, dets_pin.data_ptr(), sptr)
         if st not in (0, 7):
             rsp._binding.raise_for(st, ctx._h)
         return n
 
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        n_e2e = step_e2e()
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
+    if e2e_steps:
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            n_e2e = step_e2e()
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        # detections only (rdm_out = NULL): the host sees the raw samples go up and only the sparse list come back
+        step_e2e(False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e(False)
+        torch.cuda.synchronize(dev)
+        e2e_do_s = time.perf_counter() - t0
     if sampler:
         sampler.stop()
 
-    # ---- sparse detection gather over NCCL (outside the hot path, timed separately) ----------------
-    gather_ms = None
-    n_gathered = len(dets)
+    # ---- sparse detection gather over NCCL, on the device, steady state (median of 10 after one warm-up) ---------
+    gather_ms, gather_first_ms, n_gathered = None, None, len(dets)
     if world > 1:
+        step_device()
         barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        allrec, counts = rdist.gather_detections(dets, args.max_det, cpi_offset=rank * B, device=dev)
-        g1.record(stream)
-        torch.cuda.synchronize(dev)
-        gather_ms = g0.elapsed_time(g1)
+        times = []
+        for it in range(11):
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            g0.record(stream)
+            allrec, counts = rdist.gather_detections_device(ctx, cpi_offset=first, device=dev)
+            g1.record(stream)
+            torch.cuda.synchronize(dev)
+            times.append(g0.elapsed_time(g1))
+        gather_first_ms, gather_ms = times[0], statistics.median(times[1:])
         n_gathered = int(counts.sum())
-        # max over ranks of the device time and of the e2e wall time
-        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        assert allrec.shape[0] == n_gathered
+        # max over ranks of the device times and of the e2e wall times
+        vals = [ms, e2e_s or 0.0, e2e_do_s or 0.0, gather_ms, sustained[1] if sustained else 0.0]
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
+        ms, gather_ms = float(t[0]), float(t[3])
+        if e2e_s is not None:
+            e2e_s, e2e_do_s = float(t[1]), float(t[2])
+        if sustained:
+            sustained = (sustained[0], float(t[4]))
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        total_cpis = world * B * args.steps
-        value = total_cpis / (ms * 1e-3)
+        value = total_per_step * args.steps / (ms * 1e-3)
         pc_ms_per_launch = stage_ms["pc"] / max(n_chunks, 1)
         cpis_per_launch = n_stage_cpis / max(n_chunks, 1)
         achieved = ALG_BYTES_PER_CPI * cpis_per_launch / (pc_ms_per_launch * 1e-3) / 1e9 if pc_ms_per_launch > 0 else None
         stage_total = sum(stage_ms.values())
+        traffic, traffic_src = None, "not measured in this run (pass --ncu)"
+        if args.ncu and world == 1:
+            per_launch, traffic_src = ncu_dram_bytes(W["ncu_regex"], args.workload, max(16 if args.workload == "S3" else 2, 1))
+            traffic = per_launch
         line = {
             "metric": METRIC, "value": value, "unit": "CPI/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "S3 synthetic LFM DDC 4096 range x 64 PRT x 16 lanes, plan single (refDDCDataMF1), CFAR 5/7/T5/GO",
-                       "cpis_per_step_per_gpu": B, "distinct_cpis": min(args.distinct, B), "chunk_cpi": args.chunk,
-                       "l2": "inputs larger than L2 (%.0f MiB raw + %.0f MiB RDM per step)" % (B * CELLS * 4 / 2 ** 20, B * CELLS * 4 / 2 ** 20),
-                       "parallelism": "cpi-shard x%d, no hot-path collective" % world, "host_binding": numa},
+            "config": {"workload": W["name"],
+                       "cpis_per_step_per_gpu": B, "cpis_per_step_total": total_per_step, "distinct_cpis": min(distinct, B), "chunk_cpi": args.chunk,
+                       "l2": "inputs larger than L2 (%.0f MiB raw + %.0f MiB RDM per step per GPU)" % (B * CELLS * 4 / 2 ** 20, B * CELLS * 4 / 2 ** 20),
+                       "parallelism": "cpi-shard x%d (%s), no hot-path collective" % (world, args.scaling), "host_binding": numa},
             "hbm_gbs_chain": value / world * ALG_BYTES_PER_CPI / 1e9,
             "hbm_frac_chain": value / world * ALG_BYTES_PER_CPI / 1e9 / peak,
-            "roofline": {"bound": "hbm", "kernel": "pc_fft_tma_kernel (K1: int16 unpack + overlap-save pulse compression; 60 % of the chain's device time)",
+            "roofline": {"bound": "hbm", "kernel": W["kernel"],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the ncu --set full
-                         # capture profiles/r01j_ncu_full_final.txt (134.6 MB read + 215.7 MB written per 8-CPI launch)
-                         "traffic": K1_DRAM_BYTES_PER_CPI * cpis_per_launch, "traffic_source": "profiles/r01j_ncu_full_final.txt",
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_CPI * cpis_per_launch,
                          "ms_per_launch": pc_ms_per_launch,
                          "serialised_ms_per_step": ms_serial / args.steps,
                          "stage_share": {k: (v / stage_total if stage_total else None) for k, v in stage_ms.items()},
                          "stage_us_per_cpi": {k: 1e3 * v / max(n_stage_cpis, 1) for k, v in stage_ms.items()}},
-            "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "CPI/s", "h2d_bytes_per_step": B * CELLS * 4,
-                    "d2h_bytes_per_step": B * CELLS * 4 + 16 * min(n_e2e, args.max_det), "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
-            "detections_per_step": n_det, "gather_ms": gather_ms, "detections_gathered": n_gathered,
+            "detections_per_step": n_det, "gather_ms": gather_ms, "gather_first_ms": gather_first_ms, "detections_gathered": n_gathered,
+            "gather": "device-side: counts all_gather (1 x int32 per rank) + all_gather of exactly max(count) 16-byte records, median of 10" if world > 1 else None,
             "clocks": nvml.summary() if nvml else (sampler.summary() if sampler else None),
         }
+        if e2e_s:
+            line["e2e"] = {"value": total_per_step * e2e_steps / e2e_s, "unit": "CPI/s", "h2d_bytes_per_step": B * CELLS * 4,
+                           "d2h_bytes_per_step": B * CELLS * 4 + 16 * min(n_e2e, args.max_det), "steps": e2e_steps}
+            line["e2e_dets_only"] = {"value": total_per_step * e2e_steps / e2e_do_s, "unit": "CPI/s", "h2d_bytes_per_step": B * CELLS * 4,
+                                     "d2h_bytes_per_step": 16 * min(n_e2e, args.max_det), "steps": e2e_steps,
+                                     "note": "rdm_out = NULL: only the sparse detection list returns to the host"}
+        if sustained:
+            line["sustained"] = {"value": total_per_step * sustained[0] / (sustained[1] * 1e-3), "unit": "CPI/s", "steps": sustained[0],
+                                 "seconds": sustained[1] * 1e-3}
+        if parity is not None:
+            line["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
             try:
                 os.sched_setaffinity(0, ALL_CPUS)            # the CPU baseline may use every host core again
             except Exception:
                 pass
-            cps, dt = cpu_reference_rate(args.cpu_cpis)
-            loop_cps, loop_dt = cpu_loop_faithful_rate()
-            line["cpu_baseline"] = {"value": cps, "unit": "CPI/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "%d CPIs of the S3 workload through oracle/vec.py (float64, scipy.fft workers=all), %.1f s" % (args.cpu_cpis, dt),
-                                    "loop_faithful": {"value": loop_cps, "unit": "CPI/s", "cores": 1,
-                                                      "sample": "oracle/mcode.py (M-code loop structure) on 1 of 16 lanes of one CPI, %.1f s, extrapolated x16" % loop_dt}}
+            cps, dt, sample_txt = cpu_reference_rate(args.cpu_cpis)
+            line["cpu_baseline"] = {"value": cps, "unit": "CPI/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": sample_txt}
+            if args.workload == "S3":
+                loop_cps, loop_dt = cpu_loop_faithful_rate()
+                line["cpu_baseline"]["loop_faithful"] = {"value": loop_cps, "unit": "CPI/s", "cores": 1,
+                                                         "sample": "oracle/mcode.py (M-code loop structure) on 1 of 16 lanes of one CPI, %.1f s, extrapolated x16" % loop_dt}
         print(json.dumps(line))
     ctx.close()
     if world > 1:
@@ -413,17 +670,27 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpis", type=int, default=64, help="CPIs per step per GPU (64 -> 1 GiB of raw input)")
-    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic CPIs generated (tiled up to --cpis)")
+    ap.add_argument("--workload", default="S3", choices=["S3", "S5", "S1"],
+                    help="S3: BASELINE headline (default); S5: DBF long-CPI sweep with iSTC + MTI; S1: config-1 frame through the MATLAB-layout API")
+    ap.add_argument("--cpis", type=int, default=0, help="CPIs per step per GPU (0 = workload default: S3 64 -> 1 GiB of raw input, S5 4)")
+    ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic CPIs generated (tiled up to --cpis; 0 = workload default)")
     ap.add_argument("--chunk", type=int, default=0, help="CPIs per PC->MTD->CFAR pass (0 = library default)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: --cpis is the total batch, block-partitioned over ranks")
     ap.add_argument("--max-det", type=int, default=1 << 20)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--sustain", type=float, default=1.0, help="seconds of the additional sustained loop (0 = off)")
     ap.add_argument("--cpu-cpis", type=int, default=8, help="CPIs timed for the cpu_baseline object")
     ap.add_argument("--ref-cpis", type=int, default=2, help="CPIs per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of CPI 0 of the timed step")
+    ap.add_argument("--ncu", action="store_true", help="fill roofline.traffic from a short ncu sub-run of the dominant kernel")
     args = ap.parse_args()
+    if args.workload != "S1":
+        select_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "S1":
+        run_s1(args)
     else:
         run_gpu(args)
 

@@ -215,6 +215,11 @@ int rb200_chain_i16(rb200_ctx* ctx, const int16_t* raw, int n_cpi, float* rdm_ou
  * detection count/list stay in context memory until rb200_chain_fetch.                            */
 int rb200_chain_enqueue(rb200_ctx* ctx, const int16_t* raw_dev, int n_cpi, float* rdm_dev, void* stream);
 int rb200_chain_fetch(rb200_ctx* ctx, rb200_det* dets_host, int* n_det);
+/* Zero-copy view of the detection lists of the last chain call, in DEVICE memory (valid until the next chain call on this
+ * context): 2-D detections (the flags of CW/executeCFAR.m:78-89) and velocity-stage hits (:28-31), with their counts
+ * (waits for the chain to finish).  For consumers that stay on the device -- the multi-GPU gather hands these pointers to
+ * NCCL directly, no host bounce.  Counts are clipped to rb200_config.max_det.                              */
+int rb200_chain_dets_device(rb200_ctx* ctx, const rb200_det** dets_2d, int* n_2d, const rb200_det** dets_v, int* n_v);
 
 /* Device-side intermediates of the last chain call (parity tests): pulse-compressed samples as
  * float2 [cpi][lane][prt][range] for the last processed chunk.  The default chain for 64 PRT x 16 int16 lanes keeps that

@@ -65,7 +65,7 @@ EXPORTS = [
     "rb200_last_launch_count", "rb200_set_dbf", "rb200_set_cfar_segments", "rb200_set_stage_timing", "rb200_get_stage_ms", "rb200_unpack_dbf24", "rb200_chain_dbf24", "rb200_mtd_produce_windows_z", "rb200_dmx_process_z", "rb200_motion_para_measure_d", "rb200_reader_open", "rb200_reader_close",
     "rb200_reader_last_error", "rb200_reader_state", "rb200_reader_next_frame_ddc", "rb200_reader_next_frame_dbf24",
     "rb200_shared_context_acquire", "rb200_shared_context_release", "rb200_set_plan_tag", "rb200_get_plan_tag",
-    "rb200_set_debug_keep_pc",
+    "rb200_set_debug_keep_pc", "rb200_chain_dets_device",
 ]
 
 _lib = None
@@ -132,6 +132,7 @@ def load():
     lib.rb200_get_plan_tag.argtypes = [vp]
     lib.rb200_get_plan_tag.restype = C.c_uint64
     lib.rb200_set_debug_keep_pc.argtypes = [vp, C.c_int]
+    lib.rb200_chain_dets_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(C.c_int)]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

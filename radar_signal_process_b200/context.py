@@ -295,6 +295,15 @@ class Context:
             self._ck(st)
         return dets[: min(n.value, self.cfg.max_det)].copy(), n.value
 
+    def chain_dets_device(self, allow_overflow=False):
+        """Device pointers and counts of the last chain call's lists: ((ptr_2d, n_2d), (ptr_v, n_v)); no copy."""
+        p2, pv = C.c_void_p(), C.c_void_p()
+        n2, nv = C.c_int(0), C.c_int(0)
+        st = self._lib.rb200_chain_dets_device(self._h, C.byref(p2), C.byref(n2), C.byref(pv), C.byref(nv))
+        if not (st == B.ERR_OVERFLOW and allow_overflow):
+            self._ck(st)
+        return (p2.value, n2.value), (pv.value, nv.value)
+
     def set_debug_keep_pc(self, on=True):
         """Run later chain calls with the pulse-compressed intermediate in device memory (needed by debug_fetch_pc)."""
         self._ck(self._lib.rb200_set_debug_keep_pc(self._h, int(bool(on))))

@@ -1740,6 +1740,25 @@ extern "C" int rb200_chain_fetch(rb200_ctx* c, rb200_det* dets_host, int* n_det)
     return chain_fetch(c, dets_host, dets_host && is_device_ptr(dets_host), n_det, c->last_stream ? c->last_stream : c->stream);
 }
 
+extern "C" int rb200_chain_dets_device(rb200_ctx* c, const rb200_det** dets_2d, int* n_2d, const rb200_det** dets_v, int* n_v) {
+    if (!c) return RB200_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    CK(c, cudaMemcpyAsync(c->h_counts, c->counters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(c->h_counts + 3, c->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    const int cap = c->cfg.max_det;
+    const int nv = c->h_counts[0], n2 = c->cfg.cfar_range_stage ? c->h_counts[1] : 0;
+    if (dets_2d) *dets_2d = c->dets_2d.as<rb200_det>();
+    if (dets_v) *dets_v = c->dets_v.as<rb200_det>();
+    if (n_2d) *n_2d = std::min(n2, cap);
+    if (n_v) *n_v = std::min(nv, cap);
+    if (c->h_counts[3] == 2) return fail(c, RB200_ERR_CUDA, "fused chain kernel: a dependency wait timed out (internal error)");
+    if (c->h_counts[3]) return fail(c, RB200_ERR_INDEX, "executeCFAR: Index exceeds array bounds (CFAR axis shorter than 2*(ref+guard))");
+    if (nv > cap || n2 > cap) return fail(c, RB200_ERR_OVERFLOW, "detection list truncated: raise rb200_config.max_det");
+    return RB200_OK;
+}
+
 extern "C" int rb200_chain_i16(rb200_ctx* c, const int16_t* raw, int n_cpi, float* rdm_out, rb200_det* dets, int* n_det, void* stream) {
     if (!c || !raw) return fail(c, RB200_ERR_ARG, "chain: bad argument");
     cudaSetDevice(c->device);
