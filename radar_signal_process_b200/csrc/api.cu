@@ -145,9 +145,8 @@ struct EnvSwitches {
     int chunk = 0;              // RB200_CHUNK
     int slots = 0;              // RB200_SLOTS (0 = default)
     bool no_tma = false, no_tma_mtd = false, no_fused = false, no_fused_v = false, mega = false, no_cfar_tile = false;
-    bool onepass = false;       // RB200_ONEPASS=1: the single-pass kernel (PC intermediate in shared memory); measured slower than
-                                // the slot pipeline on B200 (profiles/r02_onepass.md), so it is opt-in
-    bool op_trace = false;      // RB200_OP_TRACE: clock stamps of CTA 0 of the last single-pass launch -> gpurun_out/op_trace.bin
+    bool no_pcw = false;        // RB200_NO_PCW=1: the CTA-wide pc_fft_tma_kernel instead of the warp-private pcw_kernel
+    bool onepass = false;       // RB200_ONEPASS=1: the single-pass kernel (PC intermediate in shared memory, onepass_kernel.cu)
     int op_dbg = 0;             // RB200_OP_DBG: timing experiments of the single-pass kernel (results are wrong)
     void read() {
         auto flag = [](const char* n) { const char* v = getenv(n); return v != nullptr && v[0] != 0 && !(v[0] == '0' && v[1] == 0); };
@@ -156,6 +155,7 @@ struct EnvSwitches {
         chunk = num("RB200_CHUNK");
         slots = num("RB200_SLOTS");
         no_tma = flag("RB200_NO_TMA");
+        no_pcw = flag("RB200_NO_PCW");
         no_tma_mtd = flag("RB200_NO_TMA_MTD");
         no_fused = flag("RB200_NO_FUSED");
         no_fused_v = flag("RB200_NO_FUSED_V");
@@ -163,7 +163,6 @@ struct EnvSwitches {
         no_cfar_tile = flag("RB200_NO_CFAR_TILE");
         onepass = flag("RB200_ONEPASS");
         op_dbg = num("RB200_OP_DBG");
-        op_trace = flag("RB200_OP_TRACE");
     }
 };
 
@@ -187,7 +186,6 @@ struct rb200_ctx {
     DevBuf raw, pc, rdm, dets_v, dets_2d, counters, vmask, errflag, colmask;
     DevBuf dbf_w;                  // DBF weights float2 [beam][channel]; dbf_beams = 0 when off
     int dbf_beams = 0;
-    DevBuf op_trace;
     DevBuf ring, megactr;          // fused persistent chain: L2-resident PC ring, work / completion counters
     bool last_was_mega = false;
     bool last_was_onepass = false;
@@ -203,7 +201,9 @@ struct rb200_ctx {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
         DevBuf pc, colmask, vlist, count, raw, rdm, beams;
-        DevBuf op_ring, op_flags;      // single-pass kernel: de-interleaved input ring and team hand-shake flags of this slot
+        DevBuf op_planar;              // single-pass kernel: de-interleaved lane planes of this slot's chunk
+        size_t op_planar_cap = 0;      // geometry the pad columns of op_planar were initialised for
+        int op_R = 0, op_V = 0;
     };
     static const int kMaxSlots = 4;
     Slot slots[kMaxSlots];
@@ -436,7 +436,15 @@ static int run_pc(rb200_ctx* ctx, const Plan& plan, bool wire, const void* in, f
         const int lt = pc_tile_lanes(c.nt, wire);
         const int n_groups = wire ? n_groups_wire : (n_lines + lt - 1) / lt;
         if (n_groups <= 0) continue;
-        if (wire && C == 16 && c.nt == 256 && plan.h_entries <= 2048 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && !ctx->env.no_tma)
+        bool pcw_ok = wire && c.nt == 256 && plan.classes.size() == 1 && !ctx->env.no_tma && !ctx->env.no_pcw &&
+                      (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+        if (pcw_ok) {
+            for (auto& sp : plan.segs) pcw_ok &= (sp.nt == 256);
+            pcw_ok = pcw_ok && pcw_plan_supported(p, (int)plan.segs.size(), plan.h_entries);
+        }
+        if (pcw_ok)
+            CK(ctx, launch_pcw(p, c.n_tiles, n_groups, ctx->n_sms, plan.h_entries, st));
+        else if (wire && C == 16 && c.nt == 256 && plan.h_entries <= 2048 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && !ctx->env.no_tma)
             CK(ctx, launch_pc_fft_tma(p, c.n_tiles, n_groups, ctx->n_sms, ctx->pc_ctas_per_sm, plan.h_entries, st));
         else CK(ctx, launch_pc_fft(c.nt, wire, p, c.n_tiles, n_groups, st));
         ctx->launches++;
@@ -1423,7 +1431,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     //      whole PRT, default velocity windows; the pulse-compressed intermediate stays in shared memory
     bool onepass = false;
     int op_V = 0, op_tiles = 0;
-    if (fused && c->env.onepass && !c->keep_pc && c->coop_launch && C == 16 && Cin == 16 && !planar_in && c->gain_n == 0 && c->plan.valid &&
+    if (fused && c->env.onepass && !c->keep_pc && C == 16 && Cin == 16 && !planar_in && c->gain_n == 0 && c->plan.valid &&
         c->plan.segs.size() == 1 && c->plan.classes.size() == 1 && c->plan.classes[0].nt == 256 && (R % 4) == 0) {
         const PcSegDev& d = c->plan.segs[0].d;
         const bool whole = d.in_start == 0 && d.out_start == 0 && d.in_len == R && d.out_len == R && d.pre == 0 && d.rot == 0 && d.h_off == 0;
@@ -1538,9 +1546,14 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
             rb200_ctx::Slot& sl = c->slots[i];
             if (!onepass) CK(c, sl.pc.ensure((size_t)G * cpi_cells * sizeof(float2)));
             else {
-                const int teams = onepass_teams(c->n_sms, G * op_tiles);
-                CK(c, sl.op_ring.ensure(onepass_ring_bytes(teams)));
-                CK(c, sl.op_flags.ensure((size_t)teams * 16 * sizeof(int)));
+                const size_t pb = onepass_planar_bytes(G, R, op_V);
+                CK(c, sl.op_planar.ensure(pb));
+                if (sl.op_planar_cap != sl.op_planar.cap || sl.op_R != R || sl.op_V != op_V) {
+                    CK(c, onepass_planar_init(sl.op_planar.p, sl.op_planar.cap, st));
+                    sl.op_planar_cap = sl.op_planar.cap;
+                    sl.op_R = R;
+                    sl.op_V = op_V;
+                }
             }
             CK(c, sl.colmask.ensure((size_t)G * C * R * sizeof(unsigned long long)));
             CK(c, sl.vlist.ensure((size_t)k.max_det * sizeof(rb200_det)));
@@ -1581,19 +1594,15 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         if (onepass) {
             OnePassParams op;
             memset(&op, 0, sizeof op);
-            op.raw = reinterpret_cast<const int*>(raw_chunk);
             op.rdm = rdm_chunk;
             op.hperm = c->plan.hperm.as<float2>();
             op.tw = c->plan.classes[0].tw.as<float2>();
-            op.ring = sl.op_ring.as<int>();
-            op.flags = sl.op_flags.as<int>();
             op.colmask = sl.colmask.as<unsigned long long>();
             op.dets = sl.vlist.p;
             op.det_count = sl.count.as<int>();
             op.err_flag = c->errflag.as<int>();
             op.max_det = k.max_det;
             op.R = R; op.V = op_V; op.n_tiles = op_tiles; op.n_cpi = g;
-            op.n_teams = onepass_teams(c->n_sms, g * op_tiles);
             op.cpi0 = c0;
             op.meth_v = k.cfar_method_v;
             op.tv_over_ref = m64.tv_over_ref;
@@ -1603,13 +1612,9 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
             }
             op.segs = c->cfar_segs;
             op.dbg = c->env.op_dbg;
-            if (c->env.op_trace) {
-                CK(c, c->op_trace.ensure(32 * 12 * 16 * sizeof(unsigned long long)));
-                CK(c, cudaMemsetAsync(c->op_trace.p, 0, 32 * 12 * 16 * sizeof(unsigned long long), cs));
-                op.trace = c->op_trace.as<unsigned long long>();
-            }
-            CK(c, cudaMemsetAsync(sl.op_flags.p, 0, (size_t)op.n_teams * 16 * sizeof(int), cs));
-            CK(c, launch_onepass(op, cs));
+            CK(c, launch_deinterleave(raw_chunk, sl.op_planar.p, g, R, op_V, cs));
+            c->launches++;
+            CK(c, launch_onepass(op, sl.op_planar.p, c->n_sms, cs));
             c->launches++;
             if (timed) { stage_event(c, cs); stage_event(c, cs); }      // "pc" = the whole single-pass kernel, "mtd" = 0
             cp.cpi0 = c0;
@@ -1710,12 +1715,6 @@ static int chain_fetch(rb200_ctx* c, rb200_det* dets, bool dets_on_device, int* 
     CK(c, cudaMemcpyAsync(c->h_counts, c->counters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(c, cudaMemcpyAsync(c->h_counts + 3, c->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
-    if (c->env.op_trace && c->op_trace.p) {
-        std::vector<unsigned long long> tr(32 * 12 * 16);
-        if (cudaMemcpy(tr.data(), c->op_trace.p, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
-            if (FILE* f = fopen("gpurun_out/op_trace.bin", "wb")) { fwrite(tr.data(), sizeof(unsigned long long), tr.size(), f); fclose(f); }
-        }
-    }
     const int nv = c->h_counts[0], n2 = c->cfg.cfar_range_stage ? c->h_counts[1] : 0;
     if (n_det) *n_det = nv + n2;
     if (c->h_counts[3] == 2) return fail(c, RB200_ERR_CUDA, "fused chain kernel: a dependency wait timed out (internal error)");

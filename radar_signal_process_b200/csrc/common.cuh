@@ -136,24 +136,21 @@ struct Chain64Params {
     int* err_flag;
 };
 
-// single-pass chain for P = 64, 16 interleaved lanes (onepass_kernel.cu)
+// single-pass chain for P = 64, 16 interleaved lanes (onepass_kernel.cu); the input arrives through a tensor map of the
+// de-interleaved lane planes (a separate kernel argument)
 struct OnePassParams {
-    const int* raw;                 // wire int16 pairs [cpi][prt][range][16 lanes] of this launch (16-byte aligned)
-    float* rdm;                     // [cpi][lane][v][range] of this launch (16-byte aligned)
+    float* rdm;                     // [cpi][lane][v][range] of this launch
     const float2* hperm;            // reference spectrum of the single MF segment, position q*16 + k <-> bin q + 16*k, times scale/256
     const float2* tw;               // tw[k*16 + u] = exp(-2*pi*i*u*k/256)
-    int* ring;                      // de-interleaved input ring: [team][4 slots][16 lanes][64 prt][272] words
-    int* flags;                     // [team][16]: rounds produced by each member (zeroed before the launch)
     unsigned long long* colmask;    // [cpi*16 + lane][R]: bit v = velocity hit at (v, r)
     void* dets;                     // rb200_det list of velocity hits (per-slot scratch list)
     int* det_count;
     int* err_flag;
     int max_det;
-    int R, V, n_tiles, n_cpi, n_teams, cpi0;
+    int R, V, n_tiles, n_cpi, cpi0;
     int meth_v;
     float tv_over_ref;
-    unsigned long long* trace;      // RB200_OP_TRACE: clock64 stamps of CTA 0, [item < 32][warp][16 events] (null = off)
-    int dbg;                        // timing experiments only (RB200_OP_DBG): 1 skip Doppler, 2 skip transforms, 4 skip de-interleave
+    int dbg;                        // timing experiments only (RB200_OP_DBG): 1 skip the Doppler column work, 2 skip the transforms
     float win[64];                  // Kaiser window
     float keep[64];                 // 0 for zero-velocity rows, 1 elsewhere (per output row)
     CfarSegs segs;

@@ -14,6 +14,9 @@ cudaError_t launch_pc_fft(int nt, bool wire, const PcParams& p, int n_tiles, int
 // persistent TMA-prefetch variant: wire format, 16 channels, 256-sample tiles
 // h_entries: float2 entries of PcParams::hperm to keep resident in shared memory (all segment spectra)
 cudaError_t launch_pc_fft_tma(const PcParams& p, int n_tiles, int n_groups, int n_sms, int ctas_per_sm, int h_entries, cudaStream_t st);
+// warp-private variant (pcw_kernel.cu): one CTA per SM, 16 warps, two lines per thread, tensor-map TMA with 128-byte swizzle
+bool pcw_plan_supported(const PcParams& p, int n_segs, int h_entries);
+cudaError_t launch_pcw(const PcParams& p, int n_tiles, int n_groups, int n_sms, int h_entries, cudaStream_t st);
 cudaError_t launch_pc_direct(bool wire, const PcParams& p, const float2* taps, int seg_idx, int out_len, int n_lines, cudaStream_t st);
 cudaError_t launch_pc_zero_cols(float2* out, size_t n_lines, int R, int c0, int c1, cudaStream_t st);
 cudaError_t launch_unpack(const int16_t* raw, float2* out, int n_groups, int P, int R, int C, cudaStream_t st);
@@ -43,9 +46,11 @@ cudaError_t launch_chain64(const Chain64Params& q, int n_sms, cudaStream_t st);
 // ---- single-pass chain for P = 64, 16 lanes: unpack + PC + MTD + 0-v + velocity CFAR with the PC intermediate in shared memory
 // (onepass_kernel.cu)
 int onepass_tile_valid(int n_taps);                 // V: valid lags per 256-sample tile (multiple of 4, <= 192)
-int onepass_teams(int n_sms, int n_tile_groups);    // teams of 16 CTAs
-size_t onepass_ring_bytes(int n_teams);
-cudaError_t launch_onepass(const OnePassParams& p, cudaStream_t st);
+int onepass_planar_pitch(int R, int V);             // 8-byte elements per (lane, PRT pair) row of the lane planes
+size_t onepass_planar_bytes(int n_cpi, int R, int V);
+cudaError_t onepass_planar_init(void* planar, size_t bytes, cudaStream_t st);     // pad columns = offset-binary zero (once per allocation)
+cudaError_t launch_deinterleave(const void* raw, void* planar, int n_cpi, int R, int V, cudaStream_t st);   // wire -> lane planes
+cudaError_t launch_onepass(const OnePassParams& p, void* planar, int n_sms, cudaStream_t st);
 
 // ---- K3 CFAR (cfar_kernels.cu)
 // chain variant: float RDM [slab][V][R] row-major -> velocity-hit list + 2-D list (+ optional dense uint8 flags)
