@@ -36,14 +36,14 @@ WORKLOADS = {
                synth=dict(seed0=1234, r_lo=100, r_hi=3900, exclude=(-1, 0)),
                name="S3 synthetic LFM DDC 4096 range x 64 PRT x 16 lanes, plan single (refDDCDataMF1), CFAR 5/7/T5/GO",
                metric="CPI frames/s (PC->MTD->0v->CFAR, 64 PRT x 4096 range x 16 lanes int16 DDC)",
-               kernel="pc_fft_tma_kernel (K1: int16 unpack + overlap-save pulse compression; the largest share of the chain's device time)",
-               ncu_regex="pc_fft_tma"),
+               kernel="pcw_kernel (K1: int16 unpack + overlap-save pulse compression, warp-private lines; the largest share of the chain's device time)",
+               ncu_regex="pcw_kernel"),
     "S5": dict(P=256, R=16384, C=16, ref="REF_DBF", cfar=(5, 7, 7.0, 0, 5, 7, 7.0, 0, 0, 1), mti=30, stc=True, cpis=4, distinct=1,
                synth=dict(seed0=5000, r_lo=100, r_hi=16384 - 200, exclude=(-3, -2, -1, 0, 1, 2, 3)),
                name="S5 DBF mode 16384 range x 256 PRT x 16 lanes, refDBFDataMF1, iSTC + MTI(30), CFAR 5/7/T7/GO",
                metric="CPI frames/s (iSTC->PC->MTI->MTD->0v->CFAR, 256 PRT x 16384 range x 16 lanes int16)",
-               kernel="pc_fft_tma_kernel (K1: int16 unpack + iSTC + overlap-save pulse compression)",
-               ncu_regex="pc_fft_tma"),
+               kernel="pcw_kernel (K1: int16 unpack + iSTC + overlap-save pulse compression, warp-private lines)",
+               ncu_regex="pcw_kernel"),
 }
 W = dict(WORKLOADS["S3"])                 # the active workload (set in main)
 P, R, C = W["P"], W["R"], W["C"]

@@ -145,6 +145,7 @@ struct EnvSwitches {
     int chunk = 0;              // RB200_CHUNK
     int slots = 0;              // RB200_SLOTS (0 = default)
     bool no_tma = false, no_tma_mtd = false, no_fused = false, no_fused_v = false, mega = false, no_cfar_tile = false;
+    bool coexist = false;       // RB200_COEXIST=1: 12-warp pcw_kernel + one mtd64_tma CTA per SM, so that K1 of chunk i+1 and K2 of chunk i share the SMs
     bool no_pcw = false;        // RB200_NO_PCW=1: the CTA-wide pc_fft_tma_kernel instead of the warp-private pcw_kernel
     bool onepass = false;       // RB200_ONEPASS=1: the single-pass kernel (PC intermediate in shared memory, onepass_kernel.cu)
     int op_dbg = 0;             // RB200_OP_DBG: timing experiments of the single-pass kernel (results are wrong)
@@ -156,6 +157,7 @@ struct EnvSwitches {
         slots = num("RB200_SLOTS");
         no_tma = flag("RB200_NO_TMA");
         no_pcw = flag("RB200_NO_PCW");
+        coexist = flag("RB200_COEXIST");
         no_tma_mtd = flag("RB200_NO_TMA_MTD");
         no_fused = flag("RB200_NO_FUSED");
         no_fused_v = flag("RB200_NO_FUSED_V");
@@ -443,7 +445,7 @@ static int run_pc(rb200_ctx* ctx, const Plan& plan, bool wire, const void* in, f
             pcw_ok = pcw_ok && pcw_plan_supported(p, (int)plan.segs.size(), plan.h_entries);
         }
         if (pcw_ok)
-            CK(ctx, launch_pcw(p, c.n_tiles, n_groups, ctx->n_sms, plan.h_entries, st));
+            CK(ctx, launch_pcw(p, c.n_tiles, n_groups, ctx->n_sms, plan.h_entries, ctx->env.coexist, st));
         else if (wire && C == 16 && c.nt == 256 && plan.h_entries <= 2048 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && !ctx->env.no_tma)
             CK(ctx, launch_pc_fft_tma(p, c.n_tiles, n_groups, ctx->n_sms, ctx->pc_ctas_per_sm, plan.h_entries, st));
         else CK(ctx, launch_pc_fft(c.nt, wire, p, c.n_tiles, n_groups, st));
@@ -656,6 +658,7 @@ extern "C" int rb200_create(rb200_ctx** out, int device, const rb200_config* cfg
     cudaDeviceGetAttribute(&c->coop_launch, cudaDevAttrCooperativeLaunch, device);
     if (const char* e1 = getenv("RB200_PC_CTAS")) c->pc_ctas_per_sm = atoi(e1);
     if (const char* e2 = getenv("RB200_MTD_CTAS")) c->mtd_ctas_per_sm = atoi(e2);
+    else if (c->env.coexist) c->mtd_ctas_per_sm = 1;
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
@@ -1362,13 +1365,15 @@ extern "C" int rb200_motion_para_measure_d(rb200_ctx* c, const double* mtd_sum, 
 static int chunk_size(const rb200_ctx* c, bool host_staged = false) {
     int g = c->env.chunk ? c->env.chunk : c->cfg.chunk_cpi;
     if (g <= 0) {
-        // default: ~0.5 GB of raw+PC+RDM per chunk (S3: 8 CPIs).  Measured on B200: per-launch overheads dominate below
-        // 4 CPIs per chunk and the PC intermediate is not L2-resident at any practical chunk size (profiles/README.md)
+        // default for device-resident batches: ~2.1 GB of raw+PC+RDM per chunk (S3: 32 CPIs).  Every launch of the persistent
+        // kernels costs a prologue and a partly filled last round (measured with pcw_kernel, S3, stage times per CPI:
+        // chunk 8 -> 14.5 / 9.7 / 2.3 us, chunk 32 -> 13.0 / 8.8 / 1.4 us), and the PC intermediate is not L2-resident
+        // at any practical chunk size (profiles/README.md)
         const double per_cpi = (double)c->cfg.n_prt * c->cfg.n_range * (c->dbf_beams ? c->dbf_beams : c->cfg.n_lanes) * 16.0;
-        g = (int)std::floor(540e6 / per_cpi);
-        // host buffers: the call is PCIe-bound and the first H2D / last D2H of a call cannot overlap anything, so halve
-        // the chunk (measured: 2.63 k -> 2.71 k CPI/s end to end; 49 GB/s each way is the box's full-duplex ceiling)
-        if (host_staged) g = std::max(1, g / 2);
+        g = (int)std::floor(2150e6 / per_cpi);
+        // host buffers: the call is PCIe-bound and the first H2D / last D2H of a call cannot overlap anything, so keep
+        // the chunks small (S3: 4 CPIs; measured: 2.63 k -> 2.71 k CPI/s end to end against 8-CPI chunks)
+        if (host_staged) g = std::max(1, g / 8);
     }
     // grid.y carries (CPIs x lanes) slabs and, on the DBF path, (CPIs x PRTs) groups: keep both inside the 65535 limit
     const int lanes = std::max(1, std::max(c->cfg.n_lanes, c->dbf_beams));
@@ -1619,7 +1624,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
             if (timed) { stage_event(c, cs); stage_event(c, cs); }      // "pc" = the whole single-pass kernel, "mtd" = 0
             cp.cpi0 = c0;
             CK(c, launch_cfar_r64(rdm_chunk, cp, (float)k.cfar_t_r, sl.vlist.p, sl.count.as<int>(), c->dets_v.p, c->dets_2d.p,
-                                  c->counters.as<int>(), sl.colmask.as<unsigned long long>(), R, c->errflag.as<int>(), c->n_sms, cs));
+                                  c->counters.as<int>(), sl.colmask.as<unsigned long long>(), R, c->errflag.as<int>(), c->n_sms * 16, cs));
             c->launches++;
             if (rdm_host)
                 CK(c, cudaMemcpyAsync(rdm_host + (size_t)c0 * cpi_cells, rdm_chunk, (size_t)g * cpi_cells * sizeof(float), cudaMemcpyDeviceToHost, cs));
@@ -1661,7 +1666,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
             c->launches++;
             if (timed) stage_event(c, cs);
             CK(c, launch_cfar_r64(rdm_chunk, cp, (float)k.cfar_t_r, sl.vlist.p, sl.count.as<int>(), c->dets_v.p, c->dets_2d.p,
-                                  c->counters.as<int>(), sl.colmask.as<unsigned long long>(), R, c->errflag.as<int>(), c->n_sms, cs));
+                                  c->counters.as<int>(), sl.colmask.as<unsigned long long>(), R, c->errflag.as<int>(), c->n_sms * 16, cs));
             c->launches++;
         } else {
             // hits of this chunk start where the list currently ends

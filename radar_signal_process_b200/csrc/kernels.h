@@ -16,7 +16,7 @@ cudaError_t launch_pc_fft(int nt, bool wire, const PcParams& p, int n_tiles, int
 cudaError_t launch_pc_fft_tma(const PcParams& p, int n_tiles, int n_groups, int n_sms, int ctas_per_sm, int h_entries, cudaStream_t st);
 // warp-private variant (pcw_kernel.cu): one CTA per SM, 16 warps, two lines per thread, tensor-map TMA with 128-byte swizzle
 bool pcw_plan_supported(const PcParams& p, int n_segs, int h_entries);
-cudaError_t launch_pcw(const PcParams& p, int n_tiles, int n_groups, int n_sms, int h_entries, cudaStream_t st);
+cudaError_t launch_pcw(const PcParams& p, int n_tiles, int n_groups, int n_sms, int h_entries, bool shared_sm, cudaStream_t st);
 cudaError_t launch_pc_direct(bool wire, const PcParams& p, const float2* taps, int seg_idx, int out_len, int n_lines, cudaStream_t st);
 cudaError_t launch_pc_zero_cols(float2* out, size_t n_lines, int R, int c0, int c1, cudaStream_t st);
 cudaError_t launch_unpack(const int16_t* raw, float2* out, int n_groups, int P, int R, int C, cudaStream_t st);

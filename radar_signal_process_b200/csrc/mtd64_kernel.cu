@@ -285,6 +285,11 @@ cudaError_t launch_mtd64_tma(const Mtd64Params& p, int n_slabs, int n_sms, int c
     static size_t configured[64] = {};
     cudaError_t ce = ensure_dynamic_smem(mtd64_tma_kernel<5, 7, 0, true>, smem, configured);
     if (ce != cudaSuccess) return ce;
+    static bool carve = false;
+    if (!carve) {       // lets a CTA of this kernel join an SM that pcw_shared_kernel configured for the maximum carve-out
+        cudaFuncSetAttribute(mtd64_tma_kernel<5, 7, 0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve = true;
+    }
     const int per_sm = std::max(1, std::min(ctas_per_sm, RB200_MTD64_MINB));
     const int grid = (int)std::min<long long>(n_items, (long long)n_sms * per_sm);
     mtd64_tma_kernel<5, 7, 0, true><<<grid, 128, smem, st>>>(p, tiles_per_slab, (int)n_items);

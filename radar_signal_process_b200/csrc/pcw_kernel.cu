@@ -25,9 +25,8 @@
 namespace rb {
 
 namespace pcw {
-constexpr int kWarps = 16;
-constexpr int kThreads = 32 * kWarps;
-constexpr int kSlots = 4;                 // staging slots; warps 4s .. 4s+3 work on slot s
+constexpr int kWarpsFull = 16;            // alone on the SM: 16 warps, 128 registers, 4 staging slots
+constexpr int kWarpsShared = 12;          // next to one mtd64_tma CTA (RB200_COEXIST): 12 warps, 112 registers, 3 staging slots
 constexpr int kNT = 256;
 constexpr int kLanes = 16;
 constexpr int kTileBytes = kNT * kLanes * 4;          // 16 384
@@ -43,11 +42,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                  : "memory");
 }
 
-template <bool GAIN>
-__global__ void __launch_bounds__(pcw::kThreads, 1)
-pcw_kernel(const __grid_constant__ PcParams p, const __grid_constant__ CUtensorMap tmap, int n_items, int n_tiles, int h_entries) {
+template <bool GAIN, int kWarps>
+__device__ __forceinline__ void pcw_body(const PcParams& p, const CUtensorMap& tmap, int n_items, int n_tiles, int h_entries) {
     using namespace pcw;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr int kSlots = kWarps / 4;        // staging slots; warps 4s .. 4s+3 work on slot s
+    constexpr int kThreads = 32 * kWarps;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     // the 128-byte swizzle pattern repeats every 1024 bytes of SHARED address: align the slots explicitly
     unsigned char* const smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* tiles = smem_al;                                                          // [4 slots][16 KB], swizzled rows of 128 B
@@ -178,6 +178,19 @@ pcw_kernel(const __grid_constant__ PcParams p, const __grid_constant__ CUtensorM
     }
 }
 
+template <bool GAIN>
+__global__ void __launch_bounds__(32 * pcw::kWarpsFull, 1)
+pcw_kernel(const __grid_constant__ PcParams p, const __grid_constant__ CUtensorMap tmap, int n_items, int n_tiles, int h_entries) {
+    pcw_body<GAIN, pcw::kWarpsFull>(p, tmap, n_items, n_tiles, h_entries);
+}
+// 12 warps x 112 registers + 159 KB of shared memory leave room for one 128-thread mtd64_tma CTA (166 registers, 64 KB) on the
+// same SM: the fp32-bound transform of chunk i+1 then runs beside the HBM-bound Doppler kernel of chunk i
+template <bool GAIN>
+__global__ void __maxnreg__(112)
+pcw_shared_kernel(const __grid_constant__ PcParams p, const __grid_constant__ CUtensorMap tmap, int n_items, int n_tiles, int h_entries) {
+    pcw_body<GAIN, pcw::kWarpsShared>(p, tmap, n_items, n_tiles, h_entries);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 bool pcw_plan_supported(const PcParams& p, int n_segs, int h_entries) {
@@ -212,19 +225,38 @@ static cudaError_t encode_wire_map(CUtensorMap* map, const void* in, int R, int 
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-cudaError_t launch_pcw(const PcParams& p, int n_tiles, int n_groups, int n_sms, int h_entries, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)pcw::kSlots * pcw::kTileBytes + (size_t)pcw::kWarps * pcw::kExBytes + 256 * sizeof(float2) +
+cudaError_t launch_pcw(const PcParams& p, int n_tiles, int n_groups, int n_sms, int h_entries, bool shared_sm, cudaStream_t st) {
+    const int warps = shared_sm ? pcw::kWarpsShared : pcw::kWarpsFull;
+    const int slots = warps / 4;
+    const size_t smem = 1024 + (size_t)slots * pcw::kTileBytes + (size_t)warps * pcw::kExBytes + 256 * sizeof(float2) +
                         (size_t)h_entries * sizeof(float2);
-    static size_t configured[2][64] = {};
-    cudaError_t ce = p.gain ? ensure_dynamic_smem(pcw_kernel<true>, smem, configured[1]) : ensure_dynamic_smem(pcw_kernel<false>, smem, configured[0]);
+    static size_t configured[4][64] = {};
+    cudaError_t ce;
+    if (shared_sm) {
+        // the SM must be configured for the maximum shared-memory carve-out while this kernel runs, or the Doppler CTA that is
+        // meant to join it (64 KB) cannot be placed until the SM drains
+        static bool carve[2] = {false, false};
+        if (!carve[p.gain ? 1 : 0]) {
+            if (p.gain) cudaFuncSetAttribute(pcw_shared_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            else cudaFuncSetAttribute(pcw_shared_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carve[p.gain ? 1 : 0] = true;
+        }
+        ce = p.gain ? ensure_dynamic_smem(pcw_shared_kernel<true>, smem, configured[3]) : ensure_dynamic_smem(pcw_shared_kernel<false>, smem, configured[2]);
+    }
+    else ce = p.gain ? ensure_dynamic_smem(pcw_kernel<true>, smem, configured[1]) : ensure_dynamic_smem(pcw_kernel<false>, smem, configured[0]);
     if (ce != cudaSuccess) return ce;
     alignas(64) CUtensorMap map;
     ce = encode_wire_map(&map, p.in, p.R, n_groups);
     if (ce != cudaSuccess) return ce;
     const int n_items = n_tiles * n_groups;
-    const int grid = std::max(1, std::min(n_sms, (n_items + pcw::kSlots - 1) / pcw::kSlots));
-    if (p.gain) pcw_kernel<true><<<grid, pcw::kThreads, smem, st>>>(p, map, n_items, n_tiles, h_entries);
-    else pcw_kernel<false><<<grid, pcw::kThreads, smem, st>>>(p, map, n_items, n_tiles, h_entries);
+    const int grid = std::max(1, std::min(n_sms, (n_items + slots - 1) / slots));
+    if (shared_sm) {
+        if (p.gain) pcw_shared_kernel<true><<<grid, 32 * warps, smem, st>>>(p, map, n_items, n_tiles, h_entries);
+        else pcw_shared_kernel<false><<<grid, 32 * warps, smem, st>>>(p, map, n_items, n_tiles, h_entries);
+    } else {
+        if (p.gain) pcw_kernel<true><<<grid, 32 * warps, smem, st>>>(p, map, n_items, n_tiles, h_entries);
+        else pcw_kernel<false><<<grid, 32 * warps, smem, st>>>(p, map, n_items, n_tiles, h_entries);
+    }
     return cudaGetLastError();
 }
 
