@@ -5,7 +5,7 @@ PKG       := radar_signal_process_b200
 CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libradar_b200.so
 NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas --expt-relaxed-constexpr
-CU_SRCS   := $(CSRC)/api.cu $(CSRC)/pc_kernels.cu $(CSRC)/pcw_kernel.cu $(CSRC)/mtd_kernels.cu $(CSRC)/mtd64_kernel.cu $(CSRC)/chain64_kernel.cu $(CSRC)/onepass_kernel.cu $(CSRC)/dbf_kernel.cu $(CSRC)/measure_kernels.cu $(CSRC)/cfar_kernels.cu $(CSRC)/layout_kernels.cu
+CU_SRCS   := $(CSRC)/api.cu $(CSRC)/pc_kernels.cu $(CSRC)/pcw_kernel.cu $(CSRC)/mtd_kernels.cu $(CSRC)/mtd64_kernel.cu $(CSRC)/mtd64_tc_kernel.cu $(CSRC)/chain64_kernel.cu $(CSRC)/onepass_kernel.cu $(CSRC)/dbf_kernel.cu $(CSRC)/measure_kernels.cu $(CSRC)/cfar_kernels.cu $(CSRC)/layout_kernels.cu
 CU_OBJS   := $(CU_SRCS:.cu=.o) $(CSRC)/reader.o
 HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/radar_b200.h
 

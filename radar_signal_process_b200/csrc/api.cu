@@ -133,6 +133,8 @@ struct MtdPlan {
     double beta = 0;
     std::vector<float> h_window;
     DevBuf window, tw;
+    DevBuf tc_mat;              // RB200_MTD_TC: split bf16 DFT matrix of mtd64_tc_kernel for the zero-velocity rows below
+    int tc_zlo = -2, tc_zhi = -2;
     int n_stages = 0;
     int radix[16];
 };
@@ -146,6 +148,7 @@ struct EnvSwitches {
     int slots = 0;              // RB200_SLOTS (0 = default)
     bool no_tma = false, no_tma_mtd = false, no_fused = false, no_fused_v = false, mega = false, no_cfar_tile = false;
     bool coexist = false;       // RB200_COEXIST=1: 12-warp pcw_kernel + one mtd64_tma CTA per SM, so that K1 of chunk i+1 and K2 of chunk i share the SMs
+    bool mtd_tc = false;        // RB200_MTD_TC=1 (with RB200_NO_FUSED=1): P = 64 Doppler transform on the tensor cores (experiment, mtd64_tc_kernel.cu)
     bool no_pcw = false;        // RB200_NO_PCW=1: the CTA-wide pc_fft_tma_kernel instead of the warp-private pcw_kernel
     bool onepass = false;       // RB200_ONEPASS=1: the single-pass kernel (PC intermediate in shared memory, onepass_kernel.cu)
     int op_dbg = 0;             // RB200_OP_DBG: timing experiments of the single-pass kernel (results are wrong)
@@ -158,6 +161,7 @@ struct EnvSwitches {
         no_tma = flag("RB200_NO_TMA");
         no_pcw = flag("RB200_NO_PCW");
         coexist = flag("RB200_COEXIST");
+        mtd_tc = flag("RB200_MTD_TC");
         no_tma_mtd = flag("RB200_NO_TMA_MTD");
         no_fused = flag("RB200_NO_FUSED");
         no_fused_v = flag("RB200_NO_FUSED_V");
@@ -584,6 +588,21 @@ static int run_mtd(rb200_ctx* ctx, const float2* in, float* out, int P, int in_l
     if (rc) return fail(ctx, rc, "fun_0v_pressing: Index in position 1 is invalid");
     p.n_stages = mp->n_stages;
     for (int i = 0; i < mp->n_stages; ++i) p.radix[i] = mp->radix[i];
+    if (ctx->env.mtd_tc && P == 64 && mti_lag == 0 && !fv) {
+        // experiment: DFT-by-GEMM on tcgen05 (window, fftshift and the zero-velocity rows are folded into the matrix)
+        if (mp->tc_zlo != p.zv_lo || mp->tc_zhi != p.zv_hi || !mp->tc_mat.p) {
+            std::vector<uint16_t> a;
+            mtd64_tc_build_matrix(mp->h_window.data(), p.zv_lo, p.zv_hi, a);
+            CK(ctx, mp->tc_mat.ensure(mtd64_tc_matrix_bytes()));
+            CK(ctx, cudaMemcpyAsync(mp->tc_mat.p, a.data(), mtd64_tc_matrix_bytes(), cudaMemcpyHostToDevice, st));
+            CK(ctx, cudaStreamSynchronize(st));
+            mp->tc_zlo = p.zv_lo;
+            mp->tc_zhi = p.zv_hi;
+        }
+        CK(ctx, launch_mtd64_tc(in, out, mp->tc_mat.p, in_ld, out_ld, cols, n_slabs, ctx->n_sms, st));
+        ctx->launches++;
+        return RB200_OK;
+    }
     if (fv) {
         p.cfar_on = 1;
         p.cf = *fv->cf;
@@ -1673,7 +1692,7 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
             if (cp.v_hi > cp.v_lo)
                 CK(c, cudaMemcpyAsync(c->counters.as<int>() + 2, c->counters.as<int>() + 0, sizeof(int), cudaMemcpyDeviceToDevice, cs));
             const bool fuse_v = cp.v_hi > cp.v_lo && mtd_fast_fuses_cfar(P) && (cp.v_hi - cp.v_lo) >= 2 * (cp.ref_v + cp.guard_v) &&
-                                !c->env.no_fused_v;
+                                !c->env.no_fused_v && !(c->env.mtd_tc && P == 64);
             FusedV fvp = {&cp, (float)k.cfar_t_v, c->dets_v.p, c->counters.as<int>() + 0, c->vmask.as<uint32_t>(), c->errflag.as<int>()};
             rc = run_mtd(c, pc_buf, rdm_chunk, P, R, R, R, g * C, k.kaiser_beta, k.zero_v_div, k.mti_lag, cs, fuse_v ? &fvp : nullptr);
             if (rc) return rc;

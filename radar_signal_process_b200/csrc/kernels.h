@@ -40,6 +40,12 @@ cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, co
                             void* dets_2d, int* gcount, const unsigned long long* colmask, int cols_ld, int* err_flag, int n_blocks,
                             cudaStream_t st);
 
+// ---- experiment: P = 64 slow-time DFT as a tcgen05 GEMM (mtd64_tc_kernel.cu), RDM only
+void mtd64_tc_build_matrix(const float* window, int zv_lo, int zv_hi, std::vector<uint16_t>& a);
+size_t mtd64_tc_matrix_bytes();
+cudaError_t launch_mtd64_tc(const float2* in, float* out, const void* a_mat, int in_ld, int out_ld, int cols, int n_slabs, int n_sms,
+                            cudaStream_t st);
+
 // ---- fused persistent PC + MTD64 + velocity CFAR for a whole batch (chain64_kernel.cu)
 cudaError_t launch_chain64(const Chain64Params& q, int n_sms, cudaStream_t st);
 

@@ -447,6 +447,26 @@ def test_chain_single_pass_kernel(lib, monkeypatch, R, B, chunk):
     assert all(np.array_equal(a[f], b[f]) and np.array_equal(a[f], c3[f]) for f in a.dtype.names)
 
 
+@pytest.mark.parametrize("R,B", [(4096, 2), (1000, 1)])
+def test_chain_tensor_core_doppler_experiment(lib, monkeypatch, R, B):
+    """RB200_MTD_TC=1 (+ RB200_NO_FUSED=1): the 64-point slow-time transform as a tcgen05 GEMM with a two-term bf16 split
+    (mtd64_tc_kernel.cu, an experiment measured against the butterfly kernels): the RDM stays inside the 1e-4 gate
+    (MP/fun_Process_MTD.m:20-26, MP/fun_0v_pressing.m:4-6) and the CFAR flags agree outside the near-threshold set."""
+    P, C = 64, 16
+    raw, _ = synth.s3_batch(B, P=P, R=R, C=C, n_targets=4, r_lo=20, r_hi=max(R - 80, 40))
+    ref = mcode.load_ref("refDDCDataMF1")
+    cfar = synth.cfar_tuple(synth.S3_CFAR)
+    out = vec.chain(raw, B, P, R, C, ("single", ref), cfar, near_tol=RTOL)
+    monkeypatch.setenv("RB200_NO_FUSED", "1")
+    monkeypatch.setenv("RB200_MTD_TC", "1")
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, max_det=1 << 20) as ctx:
+        rdm, dets, n = ctx.chain(raw, B)
+    err = _close(rdm, out["rdm"])
+    print("tensor-core Doppler RDM rel err %.2e" % err)
+    assert err > 1e-7          # the bf16 split is visible: this really is the GEMM path, not the fp32 butterflies
+    _compare_flags(dets, out, B, C, P, R, lib)
+
+
 def test_chain_single_pass_kernel_falls_back_outside_its_envelope(lib, monkeypatch):
     """With RB200_ONEPASS=1, configurations the single-pass kernel does not cover (13 lanes, a three-segment waveform, iSTC,
     R not a multiple of 4) silently take the slot pipeline and still match the oracle."""
