@@ -11,7 +11,7 @@ HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/radar_b200.h
 
 MEXDIR    := mex
 MEXBUILD  := mex/build
-MEX_NAMES := DMX_frame_process motionParaMeasure fun_MTD_produce fun_lss_pulse_compression fun_pulse_compression fun_Process_MTD fun_0v_pressing executeCFAR Function_CFAR1D_sub Function_CFAR1D_sub_fixCells
+MEX_NAMES := DMX_frame_process motionParaMeasure fun_MTD_produce fun_MTD_produce_rows fun_lss_pulse_compression fun_pulse_compression fun_Process_MTD fun_0v_pressing executeCFAR Function_CFAR1D_sub Function_CFAR1D_sub_fixCells
 MEX_SOS   := $(addprefix $(MEXBUILD)/,$(addsuffix .so,$(MEX_NAMES))) $(MEXBUILD)/fun_0v_pressing_cw.so
 SHIM      := $(MEXBUILD)/librbmexshim.so
 MEXFLAGS  := -O2 -fPIC -shared -Wall -I$(MEXDIR)/shim -I$(MEXDIR) -Wno-unused-function

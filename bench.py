@@ -285,6 +285,17 @@ def s1_chain(mod_produce, mod_zero_v, mod_cfar, echo):
     return mtd, flags
 
 
+class _CropView:
+    """What fun_MTD_produce_rows returns, indexable like the full matrix for the rows it holds (691:845)."""
+    def __init__(self, crop, full):
+        self.crop = crop
+
+    def __getitem__(self, key):
+        rows, cols = key
+        assert rows == slice(690, 845, None)
+        return self.crop[:, cols]
+
+
 def run_s1_reference(args):
     from oracle import mcode, vec
     p2, p3 = mcode.load_pulse_literals()
@@ -343,6 +354,23 @@ def run_s1(args):
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 1536 * 1031 * 16 + 155 * 868 * 8 * 4,
                     "d2h_bytes_per_step": 1536 * 1031 * 8 + 155 * 868 * 8 * 7},
             "gpu_launches": None, "detections_per_step": int(flags.sum())}
+    # crop-aware variant: fun_MTD_produce_rows(echo, 691, 845) (slow-time transform first, PC on the kept rows only) replaces
+    # fun_MTD_produce + the caller's crop; everything downstream is unchanged
+    def produce_rows(e):
+        full = np.zeros((1536, 1), dtype=np.float64)         # placeholder so that s1_chain's crop indexing stays the caller's
+        return _CropView(rsp.fun_MTD_produce_rows(e, 691, 845), full)
+    for _ in range(3):
+        s1_chain(produce_rows, rsp.fun_0v_pressing, rsp.executeCFAR, echo)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mtd_c, flags_c = s1_chain(produce_rows, rsp.fun_0v_pressing, rsp.executeCFAR, echo)
+    torch.cuda.synchronize()
+    dtc = time.perf_counter() - t0
+    line["e2e_rows"] = {"value": args.steps / dtc, "unit": "frames/s", "ms_per_step": 1e3 * dtc / args.steps,
+                        "h2d_bytes_per_step": 1536 * 1031 * 16 + 155 * 868 * 8 * 4, "d2h_bytes_per_step": 155 * 1031 * 8 + 155 * 868 * 8 * 7,
+                        "flags_equal_full_path": bool(np.array_equal(flags_c, flags)),
+                        "note": "fun_MTD_produce_rows(echo, 691, 845): Doppler first, pulse compression and D2H on the 155 kept rows only"}
     if not args.no_cpu_baseline:
         from oracle import mcode, vec
         p2, p3 = mcode.load_pulse_literals()

@@ -176,6 +176,13 @@ int rb200_zero_v_pressing_d(rb200_ctx* ctx, const double* mtd, int P, int R, int
 int rb200_mtd_produce_z(rb200_ctx* ctx, const double* echo_re, const double* echo_im, int P, int R,
                         double beta, int zero_v_div, double* out);
 
+/* MTD_crop = fun_MTD_produce(echo)(row_lo:row_hi, :)    MP/main_produce_dataset_win_xzr.m:37-40 (rows 691:845 of 1536)
+ * Same result as rb200_mtd_produce_z followed by the caller's row crop (1-based, inclusive), computed with the slow-time
+ * transform first and the pulse compression on the kept rows only; out is (row_hi-row_lo+1) x R real, column-major.
+ * Errors: RB200_ERR_INDEX when the crop leaves 1..P (MATLAB: "Index in position 1 exceeds array bounds").          */
+int rb200_mtd_produce_rows_z(rb200_ctx* ctx, const double* echo_re, const double* echo_im, int P, int R,
+                             double beta, int zero_v_div, int row_lo, int row_hi, double* out);
+
 /* F = Function_CFAR1D_sub(data, ref, save, T, method)  CW/Function_CFAR1D_sub.m:1
  * data/out are rows x cols column-major; detection runs along columns index (second dim).         */
 int rb200_cfar1d_sub_d(rb200_ctx* ctx, const double* data, int rows, int cols, int ref, int guard,

@@ -11,7 +11,7 @@ from .context import Context, dets_to_flags  # noqa: F401
 from . import waveforms  # noqa: F401
 from .matlab_api import (fun_MTD_produce, fun_lss_pulse_compression, fun_pulse_compression, fun_Process_MTD,  # noqa: F401
                          fun_0v_pressing, executeCFAR, Function_CFAR1D_sub, Function_CFAR1D_sub_fixCells,
-                         fun_MTD_produce_windows, motionParaMeasure, default_context, shutdown)
+                         fun_MTD_produce_windows, fun_MTD_produce_rows, motionParaMeasure, default_context, shutdown)
 
 __all__ = ["Context", "fun_MTD_produce", "fun_lss_pulse_compression", "fun_pulse_compression", "fun_Process_MTD",
            "fun_0v_pressing", "executeCFAR", "Function_CFAR1D_sub", "Function_CFAR1D_sub_fixCells", "dets_to_flags",

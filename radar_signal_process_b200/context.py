@@ -134,6 +134,16 @@ class Context:
         self._ck(self._lib.rb200_mtd_produce_z(self._h, _fptr(re), _fptr(im), P, R, float(beta), int(zero_v_div), _fptr(out)))
         return out
 
+    def mtd_produce_rows(self, echo, row_lo, row_hi, beta=8.0, zero_v_div=150):
+        """fun_MTD_produce(echo)(row_lo:row_hi, :) (1-based, inclusive): slow-time transform first, PC on the kept rows only."""
+        echo = np.atleast_2d(echo)
+        P, R = echo.shape
+        re, im = _split(echo)
+        out = np.zeros((max(int(row_hi) - int(row_lo) + 1, 1), R), order="F")
+        self._ck(self._lib.rb200_mtd_produce_rows_z(self._h, _fptr(re), _fptr(im), P, R, float(beta), int(zero_v_div), int(row_lo), int(row_hi),
+                                                    _fptr(out)))
+        return out
+
     def mtd_produce_windows(self, echo, win_len, row_start, beta=8.0, zero_v_div=150):
         """PC once over all rows, MTD + 0-v per window (rows row_start[i] .. row_start[i]+win_len-1, 0-based)."""
         echo = np.atleast_2d(echo)

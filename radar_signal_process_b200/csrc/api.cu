@@ -567,7 +567,8 @@ struct FusedV {            // optional velocity-CFAR fusion into the shared-memo
 };
 
 static int run_mtd(rb200_ctx* ctx, const float2* in, float* out, int P, int in_ld, int out_ld, int cols, int n_slabs,
-                   double beta, int zero_div, int mti_lag, cudaStream_t st, const FusedV* fv = nullptr) {
+                   double beta, int zero_div, int mti_lag, cudaStream_t st, const FusedV* fv = nullptr, float2* out_c = nullptr,
+                   int crop_lo = 0, int crop_hi = -1) {
     if (P < 1) return fail(ctx, RB200_ERR_ARG, "MTD: P < 1");
     if (!mtd_has_fast_path(P) && P > mtd_generic_max_p()) return fail(ctx, RB200_ERR_UNSUPPORTED, "MTD: P beyond the generic kernel's shared-memory envelope (12288)");
     MtdPlan* mp = nullptr;
@@ -588,7 +589,10 @@ static int run_mtd(rb200_ctx* ctx, const float2* in, float* out, int P, int in_l
     if (rc) return fail(ctx, rc, "fun_0v_pressing: Index in position 1 is invalid");
     p.n_stages = mp->n_stages;
     for (int i = 0; i < mp->n_stages; ++i) p.radix[i] = mp->radix[i];
-    if (ctx->env.mtd_tc && P == 64 && mti_lag == 0 && !fv) {
+    p.out_c = out_c;
+    p.crop_lo = crop_lo;
+    p.crop_hi = crop_hi;
+    if (ctx->env.mtd_tc && P == 64 && mti_lag == 0 && !fv && !out_c) {
         // experiment: DFT-by-GEMM on tcgen05 (window, fftshift and the zero-velocity rows are folded into the matrix)
         if (mp->tc_zlo != p.zv_lo || mp->tc_zhi != p.zv_hi || !mp->tc_mat.p) {
             std::vector<uint16_t> a;
@@ -1012,6 +1016,41 @@ extern "C" int rb200_mtd_produce_z(rb200_ctx* c, const double* echo_re, const do
     CK(c, launch_f32_rowmajor_to_d_colmajor(c->s_c.as<float>(), c->s_out_re.as<double>(), P, R, c->stream));
     c->launches++;
     CK(c, cudaMemcpyAsync(out, c->s_out_re.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RB200_OK;
+}
+
+// Crop-aware fun_MTD_produce: the caller keeps rows row_lo..row_hi of the result (MP/main_produce_dataset_win_xzr.m:39-40 keeps
+// 691:845 of 1536).  Pulse compression (along range, the same operator for every PRT) and the windowed slow-time transform
+// (along PRT, the same operator for every range cell) commute, so the transform runs FIRST and only the kept Doppler rows
+// are pulse-compressed, converted and returned: ~10x less PC work and ~10x fewer result bytes for the reference's crop.
+extern "C" int rb200_mtd_produce_rows_z(rb200_ctx* c, const double* echo_re, const double* echo_im, int P, int R, double beta,
+                                        int zero_v_div, int row_lo, int row_hi, double* out) {
+    if (!c || !echo_re || P < 1 || R < 1 || !out) return fail(c, RB200_ERR_ARG, "mtd_produce_rows: bad argument");
+    if (row_lo < 1 || row_hi > P || row_lo > row_hi)
+        return fail(c, RB200_ERR_INDEX, "fun_MTD_produce: Index in position 1 exceeds array bounds (row crop outside 1..P)");
+    if (!mtd_has_fast_path(P) && P > mtd_generic_max_p()) return fail(c, RB200_ERR_UNSUPPORTED, "MTD: P beyond the generic kernel's shared-memory envelope (12288)");
+    cudaSetDevice(c->device);
+    c->launches = 0;
+    const size_t n = (size_t)P * R;
+    const int nrow = row_hi - row_lo + 1;
+    const size_t nc = (size_t)nrow * R;
+    const double *dre, *dim;
+    int rc = upload_z(c, echo_re, echo_im, n, &dre, &dim);
+    if (rc) return rc;
+    CK(c, c->s_a.ensure(n * sizeof(float2)));
+    CK(c, c->s_b.ensure(nc * sizeof(float2)));
+    CK(c, c->s_out_re.ensure(nc * sizeof(double)));
+    CK(c, launch_z_to_planar(dre, dim, c->s_a.as<float2>(), P, R, c->stream));
+    c->launches++;
+    rc = run_mtd(c, c->s_a.as<float2>(), nullptr, P, R, R, R, 1, beta, zero_v_div, c->cfg.mti_lag, c->stream, nullptr, c->s_b.as<float2>(),
+                 row_lo - 1, row_hi - 1);
+    if (rc) return rc;
+    rc = run_pc(c, c->plan, false, c->s_b.p, c->s_a.as<float2>(), R, R, 1, 1, 0, nrow, nullptr, c->stream);      // kept rows only
+    if (rc) return rc;
+    CK(c, launch_abs_planar_to_d_colmajor(c->s_a.as<float2>(), c->s_out_re.as<double>(), nrow, R, c->stream));
+    c->launches++;
+    CK(c, cudaMemcpyAsync(out, c->s_out_re.p, nc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return RB200_OK;
 }

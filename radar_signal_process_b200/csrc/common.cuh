@@ -89,6 +89,8 @@ struct MtdParams {
     int radix[16];
     int in_rows;            // rows present in the input (0 = P); rows in_rows..P-1 are zero padding (fft(x, P) with P > size)
     int no_shift;           // 1: natural DFT order, no fftshift (CW/DMX_SignalProcessing_main_xzr.m:414)
+    float2* out_c;          // non-null: write the COMPLEX spectrum of output rows crop_lo..crop_hi (0-based, after the shift) as
+    int crop_lo, crop_hi;   //           planar lines [row - crop_lo][out_ld] instead of magnitudes (zero-velocity rows as zeros)
     // optional fused velocity-axis CFAR (mtd_fast_kernel only): magnitudes of the CTA's tile are kept in shared
     // memory and every thread decides R consecutive rows of its column; hits go to dets / vmask like cfar_v_kernel
     int cfar_on;

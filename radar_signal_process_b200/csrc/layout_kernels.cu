@@ -134,4 +134,29 @@ cudaError_t launch_zero_rows_d_colmajor(const double* in, double* out, int rows,
     return cudaGetLastError();
 }
 
+// |in[row][col]| (complex planar, row-major) -> out (rows x cols, column-major double)
+__global__ void abs_planar_to_d_colmajor_kernel(const float2* __restrict__ in, double* __restrict__ out, int rows, int cols) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        float v = 0.f;
+        if (r < rows && c < cols) {
+            const float2 x = in[(size_t)r * cols + c];
+            v = hypotf(x.x, x.y);
+        }
+        tile[j][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(size_t)c * rows + r] = (double)tile[threadIdx.x][j];
+    }
+}
+cudaError_t launch_abs_planar_to_d_colmajor(const float2* in, double* out, int rows, int cols, cudaStream_t st) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, 1), block(32, 8, 1);
+    abs_planar_to_d_colmajor_kernel<<<grid, block, 0, st>>>(in, out, rows, cols);
+    return cudaGetLastError();
+}
+
 }  // namespace rb

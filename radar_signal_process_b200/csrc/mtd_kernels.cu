@@ -272,7 +272,20 @@ __global__ void mtd_generic_kernel(const MtdParams p) {
         float2* tmp = a; a = b; b = tmp;
         Ns = span;
     }
-    if (ok) {
+    if (ok && p.out_c) {
+        // slow-time transform FIRST (crop-aware fun_MTD_produce): the caller pulse-compresses only the rows it keeps
+        const int half = p.no_shift ? 0 : P / 2;
+        const int nrow = p.crop_hi - p.crop_lo + 1;
+        float2* out = p.out_c + (size_t)slab * nrow * p.out_ld + r;
+        for (int m = threadIdx.y; m < P; m += blockDim.y) {
+            int row = m + half;
+            if (row >= P) row -= P;
+            if (row < p.crop_lo || row > p.crop_hi) continue;
+            float2 x = a[m * TR + rl];
+            if (row >= p.zv_lo && row <= p.zv_hi) x = make_float2(0.f, 0.f);
+            out[(size_t)(row - p.crop_lo) * p.out_ld] = x;
+        }
+    } else if (ok) {
         float* out = p.out + (size_t)slab * P * p.out_ld + r;
         const int half = p.no_shift ? 0 : P / 2;
         for (int m = threadIdx.y; m < P; m += blockDim.y) {
@@ -317,7 +330,7 @@ static cudaError_t launch_fast(const MtdParams& p, int n_slabs, cudaStream_t st)
 
 cudaError_t launch_mtd(const MtdParams& p, int n_slabs, cudaStream_t st) {
     if (p.cols <= 0 || n_slabs <= 0) return cudaSuccess;
-    const bool plain = p.in_rows == 0 && !p.no_shift;
+    const bool plain = p.in_rows == 0 && !p.no_shift && !p.out_c;
     if (p.P == 64 && plain) return launch_fast<8, 64>(p, n_slabs, st);
     if (p.P == 256 && plain) return launch_fast<16, 32>(p, n_slabs, st);
     // generic

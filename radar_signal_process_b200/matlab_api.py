@@ -108,6 +108,16 @@ def fun_MTD_produce(echo, params=None):
     return ctx.mtd_produce(echo, 8.0, 150)
 
 
+def fun_MTD_produce_rows(echo, row_lo, row_hi):
+    """``MTD = fun_MTD_produce(echo); MTD = MTD(row_lo:row_hi, :)`` (MP/main_produce_dataset_win_xzr.m:37-40, rows 691:845) in
+    one call that pulse-compresses only the kept Doppler rows (the slow-time transform runs first; both are linear and act
+    on different axes)."""
+    echo = np.atleast_2d(echo)
+    n = echo.shape[1]
+    ctx = _set_plan(("mp", n) + _key(W.PULSE2, W.PULSE3), lambda: W.segments_mp(n, W.PULSE2, W.PULSE3))
+    return ctx.mtd_produce_rows(echo, row_lo, row_hi, 8.0, 150)
+
+
 def fun_MTD_produce_windows(echo_win, win_len=1536, win_size=4):
     """The window loop of MP/main_produce_dataset_win_xzr.m:31-38 in one call: window i covers rows
     round(i*win_len/win_size)+1 ... +win_len of ``echo_win`` (two concatenated frames); pulse compression

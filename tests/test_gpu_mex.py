@@ -81,6 +81,18 @@ def test_mex_fun_MTD_produce_1arg_and_2arg():
     assert e.value.ident == "radar_b200:pc:indexOutOfRange"
 
 
+def test_mex_fun_MTD_produce_rows():
+    """fun_MTD_produce_rows(echo, lo, hi) == fun_MTD_produce(echo)(lo:hi, :) (MP/main_produce_dataset_win_xzr.m:37-40)."""
+    echo = synth.s2_frame()
+    want = mcode.fun_MTD_produce_mp(echo)
+    got = Mex("fun_MTD_produce_rows")(echo, 3.0, 6.0)
+    assert got.shape == (4, echo.shape[1])
+    assert np.max(np.abs(got - want[2:6, :])) <= 1e-4 * np.max(np.abs(want))
+    with pytest.raises(MexError) as e:
+        Mex("fun_MTD_produce_rows")(echo, 3.0, float(echo.shape[0] + 1))
+    assert e.value.ident == "radar_b200:mtdproduce:indexOutOfRange"
+
+
 def test_mex_executeCFAR_and_cfar1d_bit_identical():
     rng = np.random.default_rng(5)
     x = rng.rayleigh(1.0, size=(64, 200))

@@ -140,6 +140,30 @@ def test_fun_0v_pressing(lib, P, div):
     assert np.array_equal(got, mcode.fun_0v_pressing(m, div))
 
 
+def test_fun_MTD_produce_rows_S1(lib):
+    """Crop-aware entry (rb200_mtd_produce_rows_z): rows 691:845 of the 1536 x 1031 frame (MP/main_produce_dataset_win_xzr.m:
+    37-40) with the slow-time transform first and the pulse compression on the kept rows only, against the oracle's full
+    fun_MTD_produce cropped afterwards and against the uncropped GPU call; the MATLAB index error for a crop outside 1..P."""
+    echo = synth.s1_frame(0)
+    p2, p3 = mcode.load_pulse_literals()
+    want = vec.zero_v(vec.process_mtd(vec.lss_pc_mp(echo, p2, p3), axis=0), 150, axis=0)
+    got = lib.fun_MTD_produce_rows(echo, 691, 845)
+    assert got.shape == (155, echo.shape[1])
+    scale = np.max(np.abs(want))
+    err = np.max(np.abs(got - want[690:845, :])) / scale
+    print("S1 crop-aware RDM rel err %.2e (full-frame scale)" % err)
+    assert err <= RTOL
+    assert np.all(got[757 - 690:778 - 690, :] == 0)                  # zero-velocity rows 758:778 fall inside the crop
+    full = lib.fun_MTD_produce(echo)
+    assert np.max(np.abs(got - full[690:845, :])) <= 1e-5 * scale    # same result whichever operator runs first
+    one = lib.fun_MTD_produce_rows(echo, 1, 1)
+    assert one.shape == (1, echo.shape[1]) and np.max(np.abs(one - want[0:1, :])) <= RTOL * scale
+    with pytest.raises(lib.MatlabIndexError):
+        lib.fun_MTD_produce_rows(echo, 691, 1537)
+    with pytest.raises(lib.MatlabIndexError):
+        lib.fun_MTD_produce_rows(echo, 0, 10)
+
+
 def test_fun_MTD_produce_S1(lib):
     """Config 1 stand-in: 1536 x 1031 frame through the 1-arg API (literal pulses, segments 82/242/707)."""
     echo = synth.s1_frame(0)

@@ -8,7 +8,7 @@ import pytest
 
 from mexharness import BUILD, Mex, MexError, ROOT
 
-NAMES = ["motionParaMeasure", "fun_MTD_produce", "fun_lss_pulse_compression", "fun_pulse_compression", "fun_Process_MTD", "fun_0v_pressing",
+NAMES = ["motionParaMeasure", "fun_MTD_produce", "fun_MTD_produce_rows", "fun_lss_pulse_compression", "fun_pulse_compression", "fun_Process_MTD", "fun_0v_pressing",
          "fun_0v_pressing_cw", "executeCFAR", "Function_CFAR1D_sub", "Function_CFAR1D_sub_fixCells"]
 
 
@@ -26,6 +26,7 @@ def test_gateway_loads_and_exports_mexfunction(name):
 @pytest.mark.parametrize("name,nargs,ident", [
     ("fun_MTD_produce", 0, "radar_b200:mtdproduce:nargin"),
     ("fun_MTD_produce", 3, "radar_b200:mtdproduce:nargin"),
+    ("fun_MTD_produce_rows", 1, "radar_b200:mtdproduce:nargin"),
     ("fun_lss_pulse_compression", 4, "radar_b200:pc:nargin"),
     ("fun_pulse_compression", 1, "radar_b200:pc:nargin"),
     ("fun_Process_MTD", 2, "radar_b200:mtd:nargin"),
