@@ -299,6 +299,121 @@ __global__ void mtd_generic_kernel(const MtdParams p) {
     }
 }
 
+// Mixed-radix path for the reference's own CPI lengths: P = 16 * 16 * P3 with P3 = 6 (1536 PRTs per frame,
+// MP/main_produce_dataset_win_xzr.m:33-38) or P3 = 8 (the DMX script's 2048-point zero-padded transform,
+// CW/DMX_SignalProcessing_main_xzr.m:414).  One CTA owns TR = 8 adjacent range cells of one slab and keeps their P x 8
+// samples in shared memory; three in-place DIF stages with register butterflies (radix 16, radix 16, radix P3), task =
+// (butterfly, column) with the column fastest, so a warp touches four consecutive rows x eight columns = 256 contiguous
+// bytes per access.  Twiddle indices need no modulo: stage 1 uses w_P^(u k1) with u k1 < P, stage 2 w_P^(16 v k2).
+// Frequency k = k1 + 16 k2 + 256 k3 ends at position k1 * (P/16) + k2 * P3 + k3; the output loop maps it to its row.
+// Same options as the generic kernel: zero-padded input rows, no fftshift, MTI, complex cropped output.
+template <int P3>
+__device__ __forceinline__ void small_dft(float2 (&v)[P3], const float2* __restrict__ w /* w_P3^m, m < P3 */) {
+    float2 o[P3];
+#pragma unroll
+    for (int k = 0; k < P3; ++k) {
+        float2 acc = v[0];
+#pragma unroll
+        for (int j = 1; j < P3; ++j) {
+            const float2 t = w[(j * k) % P3];
+            acc.x = fmaf(v[j].x, t.x, acc.x); acc.x = fmaf(-v[j].y, t.y, acc.x);
+            acc.y = fmaf(v[j].x, t.y, acc.y); acc.y = fmaf(v[j].y, t.x, acc.y);
+        }
+        o[k] = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < P3; ++k) v[k] = o[k];
+}
+
+template <int P3>
+__global__ void __launch_bounds__(256, 1) mtd_mixed_kernel(const MtdParams p) {
+    constexpr int TR = 8;
+    constexpr int P = 256 * P3;
+    constexpr int S1 = P / 16;         // stride of the first radix-16 stage
+    constexpr int S2 = P3;             // stride of the second
+    extern __shared__ float2 sm[];     // [P][TR]
+    __shared__ float2 w3[P3];
+    const int c = threadIdx.x % TR;
+    const int task0 = threadIdx.x / TR;             // 0..31
+    constexpr int NT = 256 / TR;
+    const int slab = blockIdx.y;
+    const int r = blockIdx.x * TR + c;
+    const bool ok = r < p.cols;
+    const int rows_in = p.in_rows > 0 ? p.in_rows : P;
+    if (threadIdx.x < P3) w3[threadIdx.x] = __ldg(p.tw + threadIdx.x * (P / P3));
+    {
+        const float2* col = p.in + (size_t)slab * rows_in * p.in_ld + (ok ? r : 0);
+        for (int prt = task0; prt < P; prt += NT) {
+            float2 x = make_float2(0.f, 0.f);
+            if (ok && prt < rows_in) x = cscale(mtd_load(col, prt, rows_in, p.in_ld, p.mti_lag), __ldg(p.window + prt));
+            sm[prt * TR + c] = x;
+        }
+    }
+    __syncthreads();
+    // ---- stage 1: radix 16 over stride S1, twiddle w_P^(u k1)
+    for (int u = task0; u < S1; u += NT) {
+        float2 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = sm[(j * S1 + u) * TR + c];
+        Dft<16, -1>::run(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) {
+            if (k1 > 0) v[k1] = cmul(v[k1], __ldg(p.tw + u * k1));
+            sm[(k1 * S1 + u) * TR + c] = v[k1];
+        }
+    }
+    __syncthreads();
+    // ---- stage 2: inside every block k1, radix 16 over stride S2, twiddle w_S1^(v k2) = w_P^(16 v k2)
+    for (int t = task0; t < 16 * S2; t += NT) {
+        const int k1 = t / S2, vv = t - k1 * S2;
+        float2* base = sm + (size_t)(k1 * S1 + vv) * TR + c;
+        float2 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = base[j * S2 * TR];
+        Dft<16, -1>::run(v);
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+            if (k2 > 0) v[k2] = cmul(v[k2], __ldg(p.tw + 16 * vv * k2));
+            base[k2 * S2 * TR] = v[k2];
+        }
+    }
+    __syncthreads();
+    // ---- stage 3: radix P3 over the P3 consecutive entries of every block (k1, k2), then the output row
+    const int half = p.no_shift ? 0 : P / 2;
+    const int nrow = p.crop_hi - p.crop_lo + 1;
+    for (int t = task0; t < 256; t += NT) {
+        const int k1 = t >> 4, k2 = t & 15;
+        float2* base = sm + (size_t)(k1 * S1 + k2 * S2) * TR + c;
+        float2 v[P3];
+#pragma unroll
+        for (int j = 0; j < P3; ++j) v[j] = base[j * TR];
+        if (P3 == 8) {
+            float2 a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = v[j % P3];
+            dft8<-1>(a);
+#pragma unroll
+            for (int j = 0; j < P3; ++j) v[j] = a[j];
+        } else {
+            small_dft<P3>(v, w3);
+        }
+        if (!ok) continue;
+#pragma unroll
+        for (int k3 = 0; k3 < P3; ++k3) {
+            const int k = k1 + 16 * k2 + 256 * k3;
+            int row = k + half;
+            if (row >= P) row -= P;
+            const bool zero = row >= p.zv_lo && row <= p.zv_hi;
+            if (p.out_c) {
+                if (row < p.crop_lo || row > p.crop_hi) continue;
+                p.out_c[((size_t)slab * nrow + (row - p.crop_lo)) * p.out_ld + r] = zero ? make_float2(0.f, 0.f) : v[k3];
+            } else {
+                p.out[((size_t)slab * P + row) * p.out_ld + r] = zero ? 0.f : hypotf(v[k3].x, v[k3].y);
+            }
+        }
+    }
+}
+
 bool mtd_has_fast_path(int P) { return P == 64 || P == 256; }
 bool mtd_fast_fuses_cfar(int P) { return P == 64 || P == 256; }
 int mtd_generic_max_p() { return 12288; }
@@ -333,6 +448,22 @@ cudaError_t launch_mtd(const MtdParams& p, int n_slabs, cudaStream_t st) {
     const bool plain = p.in_rows == 0 && !p.no_shift && !p.out_c;
     if (p.P == 64 && plain) return launch_fast<8, 64>(p, n_slabs, st);
     if (p.P == 256 && plain) return launch_fast<16, 32>(p, n_slabs, st);
+    if (p.P == 1536 || p.P == 2048) {
+        const size_t smem = (size_t)p.P * 8 * sizeof(float2);
+        dim3 grid((p.cols + 7) / 8, n_slabs, 1);
+        if (n_slabs > 65535) return cudaErrorInvalidConfiguration;
+        static size_t configured[2][64] = {};
+        if (p.P == 1536) {
+            cudaError_t ce = ensure_dynamic_smem(mtd_mixed_kernel<6>, smem, configured[0]);
+            if (ce != cudaSuccess) return ce;
+            mtd_mixed_kernel<6><<<grid, 256, smem, st>>>(p);
+        } else {
+            cudaError_t ce = ensure_dynamic_smem(mtd_mixed_kernel<8>, smem, configured[1]);
+            if (ce != cudaSuccess) return ce;
+            mtd_mixed_kernel<8><<<grid, 256, smem, st>>>(p);
+        }
+        return cudaGetLastError();
+    }
     // generic
     int TR = 32;
     while (TR > 1 && (size_t)2 * p.P * TR * sizeof(float2) > 96 * 1024) TR >>= 1;
