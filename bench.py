@@ -272,7 +272,8 @@ S1_METRIC = "frames/s (fun_MTD_produce + main_cfar.m crop/0-v/fun_CFARflag, 1536
 
 def s1_frame(seed):
     rng = np.random.default_rng(seed)
-    return np.rint(rng.normal(0, 200, (1536, 1031))) + 1j * np.rint(rng.normal(0, 200, (1536, 1031)))
+    # column-major like the MATLAB matrix the reference hands to fun_MTD_produce (FrameDataRead_xzr.m:150-156 builds it that way)
+    return np.asfortranarray(np.rint(rng.normal(0, 200, (1536, 1031))) + 1j * np.rint(rng.normal(0, 200, (1536, 1031))))
 
 
 def s1_chain(mod_produce, mod_zero_v, mod_cfar, echo):

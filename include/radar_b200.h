@@ -183,6 +183,12 @@ int rb200_mtd_produce_z(rb200_ctx* ctx, const double* echo_re, const double* ech
 int rb200_mtd_produce_rows_z(rb200_ctx* ctx, const double* echo_re, const double* echo_im, int P, int R,
                              double beta, int zero_v_div, int row_lo, int row_hi, double* out);
 
+/* The same two entry points for INTERLEAVED complex input (MATLAB -R2018a mxGetComplexDoubles, Octave's and numpy's native
+ * storage): echo_ri holds P x R column-major (re, im) pairs; one H2D copy, no host-side split.                     */
+int rb200_mtd_produce_c(rb200_ctx* ctx, const double* echo_ri, int P, int R, double beta, int zero_v_div, double* out);
+int rb200_mtd_produce_rows_c(rb200_ctx* ctx, const double* echo_ri, int P, int R, double beta, int zero_v_div,
+                             int row_lo, int row_hi, double* out);
+
 /* F = Function_CFAR1D_sub(data, ref, save, T, method)  CW/Function_CFAR1D_sub.m:1
  * data/out are rows x cols column-major; detection runs along columns index (second dim).         */
 int rb200_cfar1d_sub_d(rb200_ctx* ctx, const double* data, int rows, int cols, int ref, int guard,

@@ -59,7 +59,7 @@ assert DET_DTYPE.itemsize == 16
 EXPORTS = [
     "rb200_version", "rb200_create", "rb200_destroy", "rb200_last_error", "rb200_get_config", "rb200_set_cfar",
     "rb200_set_waveform", "rb200_set_stc", "rb200_pulse_compression_z", "rb200_lss_pulse_compression_z",
-    "rb200_process_mtd_z", "rb200_zero_v_pressing_d", "rb200_mtd_produce_z", "rb200_mtd_produce_rows_z", "rb200_cfar1d_sub_d",
+    "rb200_process_mtd_z", "rb200_zero_v_pressing_d", "rb200_mtd_produce_z", "rb200_mtd_produce_rows_z", "rb200_mtd_produce_c", "rb200_mtd_produce_rows_c", "rb200_cfar1d_sub_d",
     "rb200_cfar1d_fix_d", "rb200_execute_cfar_d", "rb200_unpack_ddc_i16", "rb200_chain_i16",
     "rb200_chain_enqueue", "rb200_chain_fetch", "rb200_debug_fetch_pc", "rb200_last_device_ms",
     "rb200_last_launch_count", "rb200_set_dbf", "rb200_set_cfar_segments", "rb200_set_stage_timing", "rb200_get_stage_ms", "rb200_unpack_dbf24", "rb200_chain_dbf24", "rb200_mtd_produce_windows_z", "rb200_dmx_process_z", "rb200_motion_para_measure_d", "rb200_reader_open", "rb200_reader_close",
@@ -97,6 +97,8 @@ def load():
     lib.rb200_zero_v_pressing_d.argtypes = [vp, dp, C.c_int, C.c_int, C.c_int, dp]
     lib.rb200_mtd_produce_z.argtypes = [vp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_int, dp]
     lib.rb200_mtd_produce_rows_z.argtypes = [vp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, dp]
+    lib.rb200_mtd_produce_c.argtypes = [vp, dp, C.c_int, C.c_int, C.c_double, C.c_int, dp]
+    lib.rb200_mtd_produce_rows_c.argtypes = [vp, dp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, dp]
     lib.rb200_cfar1d_sub_d.argtypes = [vp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, dp]
     lib.rb200_cfar1d_fix_d.argtypes = [vp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                        C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), C.c_int, dp]

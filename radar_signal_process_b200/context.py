@@ -129,8 +129,13 @@ class Context:
     def mtd_produce(self, echo, beta=8.0, zero_v_div=150):
         echo = np.atleast_2d(echo)
         P, R = echo.shape
+        out = np.empty((P, R), order="F")
+        if np.iscomplexobj(echo):       # numpy's complex128 is interleaved: one H2D copy, no host-side split
+            z = np.asfortranarray(echo, dtype=np.complex128)
+            self._ck(self._lib.rb200_mtd_produce_c(self._h, z.ctypes.data_as(C.POINTER(C.c_double)), P, R, float(beta), int(zero_v_div),
+                                                   _fptr(out)))
+            return out
         re, im = _split(echo)
-        out = np.zeros((P, R), order="F")
         self._ck(self._lib.rb200_mtd_produce_z(self._h, _fptr(re), _fptr(im), P, R, float(beta), int(zero_v_div), _fptr(out)))
         return out
 
@@ -138,8 +143,13 @@ class Context:
         """fun_MTD_produce(echo)(row_lo:row_hi, :) (1-based, inclusive): slow-time transform first, PC on the kept rows only."""
         echo = np.atleast_2d(echo)
         P, R = echo.shape
-        re, im = _split(echo)
         out = np.zeros((max(int(row_hi) - int(row_lo) + 1, 1), R), order="F")
+        if np.iscomplexobj(echo):
+            z = np.asfortranarray(echo, dtype=np.complex128)
+            self._ck(self._lib.rb200_mtd_produce_rows_c(self._h, z.ctypes.data_as(C.POINTER(C.c_double)), P, R, float(beta), int(zero_v_div),
+                                                        int(row_lo), int(row_hi), _fptr(out)))
+            return out
+        re, im = _split(echo)
         self._ck(self._lib.rb200_mtd_produce_rows_z(self._h, _fptr(re), _fptr(im), P, R, float(beta), int(zero_v_div), int(row_lo), int(row_hi),
                                                     _fptr(out)))
         return out

@@ -994,20 +994,34 @@ extern "C" int rb200_zero_v_pressing_d(rb200_ctx* c, const double* mtd, int P, i
     return RB200_OK;
 }
 
-extern "C" int rb200_mtd_produce_z(rb200_ctx* c, const double* echo_re, const double* echo_im, int P, int R, double beta,
-                                   int zero_v_div, double* out) {
+// interleaved = false: echo_re / echo_im are split column-major arrays (mxGetPr / mxGetPi); true: echo_re points at interleaved
+// complex doubles (MATLAB -R2018a mxGetComplexDoubles, numpy complex128), echo_im is ignored
+static int upload_echo(rb200_ctx* c, const double* echo_re, const double* echo_im, bool interleaved, size_t n, const double** dre,
+                       const double** dim, int* es) {
+    if (!interleaved) { *es = 1; return upload_z(c, echo_re, echo_im, n, dre, dim); }
+    CK(c, c->s_in_re.ensure(std::max<size_t>(n, 1) * 2 * sizeof(double)));
+    CK(c, cudaMemcpyAsync(c->s_in_re.p, echo_re, n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    *dre = c->s_in_re.as<double>();
+    *dim = c->s_in_re.as<double>() + 1;
+    *es = 2;
+    return RB200_OK;
+}
+
+static int mtd_produce_impl(rb200_ctx* c, const double* echo_re, const double* echo_im, bool interleaved, int P, int R, double beta,
+                            int zero_v_div, double* out) {
     if (!c || !echo_re || P < 1 || R < 1 || !out) return fail(c, RB200_ERR_ARG, "mtd_produce: bad argument");
     cudaSetDevice(c->device);
     c->launches = 0;
     const size_t n = (size_t)P * R;
     const double *dre, *dim;
-    int rc = upload_z(c, echo_re, echo_im, n, &dre, &dim);
+    int es;
+    int rc = upload_echo(c, echo_re, echo_im, interleaved, n, &dre, &dim, &es);
     if (rc) return rc;
     CK(c, c->s_a.ensure(n * sizeof(float2)));
     CK(c, c->s_b.ensure(n * sizeof(float2)));
     CK(c, c->s_c.ensure(n * sizeof(float)));
     CK(c, c->s_out_re.ensure(n * sizeof(double)));
-    CK(c, launch_z_to_planar(dre, dim, c->s_a.as<float2>(), P, R, c->stream));
+    CK(c, launch_z_to_planar(dre, dim, c->s_a.as<float2>(), P, R, c->stream, es));
     c->launches++;
     rc = run_pc(c, c->plan, false, c->s_a.p, c->s_b.as<float2>(), R, R, 1, 1, 0, P, nullptr, c->stream);
     if (rc) return rc;
@@ -1020,12 +1034,20 @@ extern "C" int rb200_mtd_produce_z(rb200_ctx* c, const double* echo_re, const do
     return RB200_OK;
 }
 
+extern "C" int rb200_mtd_produce_z(rb200_ctx* c, const double* echo_re, const double* echo_im, int P, int R, double beta,
+                                   int zero_v_div, double* out) {
+    return mtd_produce_impl(c, echo_re, echo_im, false, P, R, beta, zero_v_div, out);
+}
+extern "C" int rb200_mtd_produce_c(rb200_ctx* c, const double* echo_ri, int P, int R, double beta, int zero_v_div, double* out) {
+    return mtd_produce_impl(c, echo_ri, nullptr, true, P, R, beta, zero_v_div, out);
+}
+
 // Crop-aware fun_MTD_produce: the caller keeps rows row_lo..row_hi of the result (MP/main_produce_dataset_win_xzr.m:39-40 keeps
 // 691:845 of 1536).  Pulse compression (along range, the same operator for every PRT) and the windowed slow-time transform
 // (along PRT, the same operator for every range cell) commute, so the transform runs FIRST and only the kept Doppler rows
 // are pulse-compressed, converted and returned: ~10x less PC work and ~10x fewer result bytes for the reference's crop.
-extern "C" int rb200_mtd_produce_rows_z(rb200_ctx* c, const double* echo_re, const double* echo_im, int P, int R, double beta,
-                                        int zero_v_div, int row_lo, int row_hi, double* out) {
+static int mtd_produce_rows_impl(rb200_ctx* c, const double* echo_re, const double* echo_im, bool interleaved, int P, int R, double beta,
+                                 int zero_v_div, int row_lo, int row_hi, double* out) {
     if (!c || !echo_re || P < 1 || R < 1 || !out) return fail(c, RB200_ERR_ARG, "mtd_produce_rows: bad argument");
     if (row_lo < 1 || row_hi > P || row_lo > row_hi)
         return fail(c, RB200_ERR_INDEX, "fun_MTD_produce: Index in position 1 exceeds array bounds (row crop outside 1..P)");
@@ -1036,12 +1058,13 @@ extern "C" int rb200_mtd_produce_rows_z(rb200_ctx* c, const double* echo_re, con
     const int nrow = row_hi - row_lo + 1;
     const size_t nc = (size_t)nrow * R;
     const double *dre, *dim;
-    int rc = upload_z(c, echo_re, echo_im, n, &dre, &dim);
+    int es;
+    int rc = upload_echo(c, echo_re, echo_im, interleaved, n, &dre, &dim, &es);
     if (rc) return rc;
     CK(c, c->s_a.ensure(n * sizeof(float2)));
     CK(c, c->s_b.ensure(nc * sizeof(float2)));
     CK(c, c->s_out_re.ensure(nc * sizeof(double)));
-    CK(c, launch_z_to_planar(dre, dim, c->s_a.as<float2>(), P, R, c->stream));
+    CK(c, launch_z_to_planar(dre, dim, c->s_a.as<float2>(), P, R, c->stream, es));
     c->launches++;
     rc = run_mtd(c, c->s_a.as<float2>(), nullptr, P, R, R, R, 1, beta, zero_v_div, c->cfg.mti_lag, c->stream, nullptr, c->s_b.as<float2>(),
                  row_lo - 1, row_hi - 1);
@@ -1053,6 +1076,15 @@ extern "C" int rb200_mtd_produce_rows_z(rb200_ctx* c, const double* echo_re, con
     CK(c, cudaMemcpyAsync(out, c->s_out_re.p, nc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return RB200_OK;
+}
+
+extern "C" int rb200_mtd_produce_rows_z(rb200_ctx* c, const double* echo_re, const double* echo_im, int P, int R, double beta,
+                                        int zero_v_div, int row_lo, int row_hi, double* out) {
+    return mtd_produce_rows_impl(c, echo_re, echo_im, false, P, R, beta, zero_v_div, row_lo, row_hi, out);
+}
+extern "C" int rb200_mtd_produce_rows_c(rb200_ctx* c, const double* echo_ri, int P, int R, double beta, int zero_v_div, int row_lo,
+                                        int row_hi, double* out) {
+    return mtd_produce_rows_impl(c, echo_ri, nullptr, true, P, R, beta, zero_v_div, row_lo, row_hi, out);
 }
 
 extern "C" int rb200_mtd_produce_windows_z(rb200_ctx* c, const double* echo_re, const double* echo_im, int P_total, int R, int win_len,

@@ -80,7 +80,7 @@ cudaError_t launch_measure(const double* sum, const double* diff, const double* 
                            const int* col_start, double* out_r, double* out_v, double* out_e, int* err_flag, cudaStream_t st);
 
 // ---- layout conversion (layout_kernels.cu): MATLAB column-major split double <-> device layouts
-cudaError_t launch_z_to_planar(const double* re, const double* im, float2* out, int rows, int cols, cudaStream_t st);          // out[row][col]
+cudaError_t launch_z_to_planar(const double* re, const double* im, float2* out, int rows, int cols, cudaStream_t st, int elem_stride = 1);          // out[row][col]
 cudaError_t launch_planar_to_z(const float2* in, double* re, double* im, int rows, int cols, cudaStream_t st);                // in[row][col]
 cudaError_t launch_abs_planar_to_d_colmajor(const float2* in, double* out, int rows, int cols, cudaStream_t st);   // |in[row][col]|
 cudaError_t launch_f32_rowmajor_to_d_colmajor(const float* in, double* out, int rows, int cols, cudaStream_t st);

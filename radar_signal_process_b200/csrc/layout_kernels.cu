@@ -10,13 +10,14 @@
 namespace rb {
 
 // in: re/im column-major rows x cols (element (i,j) at i + rows*j) -> out row-major float2 [i][j]
-__global__ void z_to_planar_kernel(const double* __restrict__ re, const double* __restrict__ im, float2* __restrict__ out, int rows, int cols) {
+// es: element stride of re / im in doubles (1 = split storage, 2 = interleaved complex with im = re + 1)
+__global__ void z_to_planar_kernel(const double* __restrict__ re, const double* __restrict__ im, float2* __restrict__ out, int rows, int cols, int es) {
     __shared__ float2 tile[32][33];
     const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
     for (int dj = threadIdx.y; dj < 32; dj += blockDim.y) {
         const int i = i0 + threadIdx.x, j = j0 + dj;
         if (i < rows && j < cols) {
-            const size_t k = (size_t)i + (size_t)rows * j;
+            const size_t k = ((size_t)i + (size_t)rows * j) * es;
             tile[dj][threadIdx.x] = make_float2((float)re[k], im ? (float)im[k] : 0.f);
         }
     }
@@ -101,9 +102,9 @@ __global__ void zero_rows_kernel(const double* __restrict__ in, double* __restri
 
 static dim3 tgrid(int rows, int cols) { return dim3((rows + 31) / 32, (cols + 31) / 32, 1); }
 
-cudaError_t launch_z_to_planar(const double* re, const double* im, float2* out, int rows, int cols, cudaStream_t st) {
+cudaError_t launch_z_to_planar(const double* re, const double* im, float2* out, int rows, int cols, cudaStream_t st, int elem_stride) {
     if (rows <= 0 || cols <= 0) return cudaSuccess;
-    z_to_planar_kernel<<<tgrid(rows, cols), dim3(32, 8), 0, st>>>(re, im, out, rows, cols);
+    z_to_planar_kernel<<<tgrid(rows, cols), dim3(32, 8), 0, st>>>(re, im, out, rows, cols, elem_stride);
     return cudaGetLastError();
 }
 cudaError_t launch_planar_to_z(const float2* in, double* re, double* im, int rows, int cols, cudaStream_t st) {
