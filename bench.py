@@ -411,7 +411,7 @@ def ncu_dram_bytes(regex, workload, cpis):
     import shutil
     if not shutil.which("ncu"):
         return None, "ncu not found"
-    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:" + regex, "-s", "2", "-c", "4",
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:" + regex, "-s", "1", "-c", "2",
            "--csv", sys.executable, os.path.abspath(__file__), "--workload", workload, "--cpis", str(cpis), "--steps", "1", "--warmup", "1",
            "--no-cpu-baseline", "--e2e-steps", "0", "--no-parity"]
     try:
@@ -419,6 +419,8 @@ def ncu_dram_bytes(regex, workload, cpis):
     except Exception as e:
         return None, "ncu failed: %s" % type(e).__name__
     rows = [r for r in csv.reader(out.splitlines()) if len(r) > 10]
+    while rows and "Metric Name" not in rows[0]:      # the profiled script's own JSON line precedes the table on stdout
+        rows.pop(0)
     if not rows:
         return None, "ncu produced no rows"
     hdr = rows[0]
@@ -638,7 +640,8 @@ def run_gpu(args):
         stage_total = sum(stage_ms.values())
         traffic, traffic_src = None, "not measured in this run (pass --ncu)"
         if args.ncu and world == 1:
-            per_launch, traffic_src = ncu_dram_bytes(W["ncu_regex"], args.workload, max(16 if args.workload == "S3" else 2, 1))
+            # same CPIs per launch as the line above, so that `traffic` and `algorithmic_bytes_per_launch` describe the same launch
+            per_launch, traffic_src = ncu_dram_bytes(W["ncu_regex"], args.workload, max(int(round(cpis_per_launch)), 1))
             traffic = per_launch
         line = {
             "metric": METRIC, "value": value, "unit": "CPI/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

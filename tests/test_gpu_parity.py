@@ -491,6 +491,28 @@ def test_chain_tensor_core_doppler_experiment(lib, monkeypatch, R, B):
     _compare_flags(dets, out, B, C, P, R, lib)
 
 
+@pytest.mark.parametrize("env", [{"RB200_COEXIST": "1"}, {"RB200_NO_PCW": "1"}])
+def test_chain_k1_variants_agree(lib, monkeypatch, env):
+    """The K1 variants behind the experiment switches -- the 12-warp pcw_shared_kernel of RB200_COEXIST (with one Doppler CTA
+    per SM) and the round-1 CTA-wide pc_fft_tma_kernel (RB200_NO_PCW) -- against the default warp-private pcw_kernel: the same
+    overlap-save arithmetic (MP/fun_pulse_compression.m:16-22), so the RDM agrees to rounding and the detections are identical
+    outside the near-threshold set of the oracle."""
+    P, R, C, B = 64, 1500, 16, 3
+    raw, _ = synth.s3_batch(B, P=P, R=R, C=C, n_targets=4, r_lo=20, r_hi=R - 80)
+    ref = mcode.load_ref("refDDCDataMF1")
+    cfar = synth.cfar_tuple(synth.S3_CFAR)
+    out = vec.chain(raw, B, P, R, C, ("single", ref), cfar, near_tol=RTOL)
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=1, max_det=1 << 20) as ctx:
+        rdm_d, dets_d, _ = ctx.chain(raw, B)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=1, max_det=1 << 20) as ctx:
+        rdm, dets, _ = ctx.chain(raw, B)
+    _close(rdm, out["rdm"])
+    _close(rdm, rdm_d, tol=1e-5)
+    _compare_flags(dets, out, B, C, P, R, lib)
+
+
 def test_chain_single_pass_kernel_falls_back_outside_its_envelope(lib, monkeypatch):
     """With RB200_ONEPASS=1, configurations the single-pass kernel does not cover (13 lanes, a three-segment waveform, iSTC,
     R not a multiple of 4) silently take the slot pipeline and still match the oracle."""
