@@ -309,7 +309,9 @@ __global__ void __launch_bounds__(op::kThreads, 1) onepass_kernel(const __grid_c
             // exchange rows = the lines' own slab rows (layout in pcw_core.cuh)
             float2* const rowA = slab + prtA * kRowC;
             float2* const rowB = rowA + kRowC;
-            pc_pair_transform(a, b, tw_sm, h_sm, n1, rowA + n1, rowB + n1, rowA + 17 * n1, rowB + 17 * n1);
+            PcTwiddles twr;
+            twr.load(tw_sm, n1);
+            pc_pair_transform(a, b, twr, h_sm, n1, rowA + n1, rowB + n1, rowA + 17 * n1, rowB + 17 * n1);
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 12; ++j)

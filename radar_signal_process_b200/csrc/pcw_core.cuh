@@ -35,20 +35,28 @@ __device__ __forceinline__ float2 unpack_tc(unsigned w) { return unpack_ob(w ^ 0
 constexpr int kPcwRowC = 272;      // complex slots per exchange row: the 16 x 16 matrix at a pitch of 17 slots
 
 // In: a[j], b[j] = x[n1 + 16 j] of the thread's two lines.  Out: a[j], b[j] = y[n1 + 16 j], y = ifft(fft(x) .* H) with
-// H = conj(FFT(taps)) * scale / 256 given as h_blk[16 j + n1] = bin n1 + 16 j, tw_sm[16 q + n1] = w256^(n1 q).
+// H = conj(FFT(taps)) * scale / 256 given as h_blk[16 j + n1] = bin n1 + 16 j, tw = w256^(n1 q) (PcTwiddles).
 // Radix-16 x 16: forward DIF, spectrum product in digit-reversed order, inverse DIT; the two exchanges go through the
 // line's own row (wA/wB = row + n1, rA/rB = row + 17 n1): element (r, c) of the 16 x 16 matrix sits at slot 17 r + c,
 // writers fill 16 consecutive slots per instruction, readers hit 16 different bank pairs, every address is base +
 // immediate.  Only __syncwarp between the phases: a row is private to the 16 threads of its line pair.
-__device__ __forceinline__ void pc_pair_transform(float2 (&a)[16], float2 (&b)[16], const float2* tw_sm, const float2* h_blk, int n1,
-                                                  float2* wA, float2* wB, const float2* rA, const float2* rB) {
-    float twx[15], twy[15];
+// the thread's twiddles w256^(n1 q), q = 1..15, as scalar pairs
+struct PcTwiddles {
+    float x[15], y[15];
+    __device__ __forceinline__ void load(const float2* tw_sm, int n1) {
 #pragma unroll
-    for (int q = 1; q < 16; ++q) {
-        const float2 w = tw_sm[q * 16 + n1];
-        twx[q - 1] = w.x;
-        twy[q - 1] = w.y;
+        for (int q = 1; q < 16; ++q) {
+            const float2 w = tw_sm[q * 16 + n1];
+            x[q - 1] = w.x;
+            y[q - 1] = w.y;
+        }
     }
+};
+
+__device__ __forceinline__ void pc_pair_transform(float2 (&a)[16], float2 (&b)[16], const PcTwiddles& tw, const float2* h_blk, int n1,
+                                                  float2* wA, float2* wB, const float2* rA, const float2* rB) {
+    const float (&twx)[15] = tw.x;
+    const float (&twy)[15] = tw.y;
     Dft<16, -1>::run(a);
     Dft<16, -1>::run(b);
 #pragma unroll

@@ -94,6 +94,8 @@ __device__ __forceinline__ void pcw_body(const PcParams& p, const CUtensorMap& t
     float2* const rowA = ex;
     float2* const rowB = ex + kPcwRowC;
 
+    PcTwiddles twr;                               // loaded once: the thread keeps its positions n1 + 16 j for every item
+    twr.load(tw_sm, n1);
     int it = 0;
 #pragma unroll 1
     for (int item = worker; item < n_items; item += stride, ++it) {
@@ -144,7 +146,7 @@ __device__ __forceinline__ void pcw_body(const PcParams& p, const CUtensorMap& t
                 b[j] = cscale(b[j], gn[GAIN ? j : 0]);
             }
         }
-        pc_pair_transform(a, b, tw_sm, h_sm + sg.h_off, n1, rowA + n1, rowB + n1, rowA + 17 * n1, rowB + 17 * n1);
+        pc_pair_transform(a, b, twr, h_sm + sg.h_off, n1, rowA + n1, rowB + n1, rowA + 17 * n1, rowB + 17 * n1);
         __syncwarp();                             // the rows are reused by the next item
         {
             const int cpi = g / p.P, prt = g - cpi * p.P;
