@@ -43,12 +43,14 @@ extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
         const size_t n2 = rb_colon_count(-tao2 / 2, ts, tao2 / 2 - ts), n3 = rb_colon_count(-tao3 / 2, ts, tao3 / 2 - ts);
         q2re = (double*)malloc((n2 + 1) * sizeof(double)); q2im = (double*)malloc((n2 + 1) * sizeof(double));
         q3re = (double*)malloc((n3 + 1) * sizeof(double)); q3im = (double*)malloc((n3 + 1) * sizeof(double));
-        for (size_t i = 0; i < n2; ++i) {                                            /* :62,68 */
-            const double t = -tao2 / 2 + ts * (double)i, ph = 2.0 * M_PI * (0.5 * K2 * (t * t));
+        rb_colon_fill(-tao2 / 2, ts, tao2 / 2 - ts, q2re);                           /* t2 = -tao2/2:ts:tao2/2-ts, :62 */
+        rb_colon_fill(-tao3 / 2, ts, tao3 / 2 - ts, q3re);                           /* :63 */
+        for (size_t i = 0; i < n2; ++i) {                                            /* :68 */
+            const double t = q2re[i], ph = 2.0 * M_PI * (0.5 * K2 * (t * t));
             q2re[i] = cos(ph); q2im[i] = sin(ph);
         }
-        for (size_t i = 0; i < n3; ++i) {                                            /* :63,69 */
-            const double t = -tao3 / 2 + ts * (double)i, ph = 2.0 * M_PI * (0.5 * K3 * (t * t));
+        for (size_t i = 0; i < n3; ++i) {                                            /* :69 */
+            const double t = q3re[i], ph = 2.0 * M_PI * (0.5 * K3 * (t * t));
             q3re[i] = cos(ph); q3im[i] = sin(ph);
         }
         pl.p2re = q2re; pl.p2im = q2im; pl.n2 = (int)n2;

@@ -85,10 +85,37 @@ static void rb_no_plots(const mxArray* flag) {
         mexWarnMsgIdAndTxt("radar_b200:plot:notReproduced", "show_PC/show_FFT/graph plotting is not reproduced by the MEX gateway");
 }
 
-/* MATLAB a:d:b element count */
+/* MATLAB a:d:b as MathWorks' published COLONOP replication builds it: rb_colon_count = number of elements, rb_colon_fill writes
+ * them symmetrically from both ends (a + k d up to the middle, c - k d down from the right end, the exact mid-point for even
+ * n), so that the ideal LFM pulses of MTD/fun_MTD_produce.m:62-69 carry MATLAB's own last bits. */
+static long rb_colon_n(double a, double d, double b, double* c_out) {
+    if (!(a == a) || !(d == d) || !(b == b) || d == 0 || (a < b && d < 0) || (b < a && d > 0)) return -1;
+    const double eps = 2.220446049250313e-16;
+    const double tol = 2.0 * eps * (fabs(a) > fabs(b) ? fabs(a) : fabs(b));
+    const double sig = d > 0 ? 1.0 : -1.0;
+    long n;
+    if (a == floor(a) && d == 1) n = (long)(floor(b) - a);
+    else if (a == floor(a) && d == floor(d)) { const double q = floor(a / d), r = a - q * d; n = (long)(floor((b - r) / d) - q); }
+    else { n = (long)floor((b - a) / d + 0.5); if (sig * (a + (double)n * d - b) > tol) n -= 1; }
+    if (n < 0) return -1;
+    double c = a + (double)n * d;
+    if (sig * (c - b) > -tol) c = b;
+    if (c_out) *c_out = c;
+    return n;
+}
 static size_t rb_colon_count(double a, double d, double b) {
-    double n = floor((b - a) / d * (1.0 + 4.0 * 2.220446049250313e-16) + 1e-10);
+    const long n = rb_colon_n(a, d, b, NULL);
     return n < 0 ? 0 : (size_t)n + 1;
+}
+static void rb_colon_fill(double a, double d, double b, double* out) {
+    double c;
+    const long n = rb_colon_n(a, d, b, &c);
+    if (n < 0) return;
+    for (long k = 0; k <= n / 2; ++k) {
+        out[k] = a + (double)k * d;
+        out[n - k] = c - (double)k * d;
+    }
+    if (n % 2 == 0) out[n / 2] = (a + c) / 2;
 }
 
 /* ---- waveform plans ---------------------------------------------------------------------------- */

@@ -110,11 +110,39 @@ def pulse1_mp():
 
 
 def matlab_colon(a, d, b):
-    """``a:d:b`` with MATLAB's tolerance on the end point."""
-    n = int(math.floor((b - a) / d * (1 + 4 * np.finfo(float).eps) + 1e-10))
+    """``a:d:b`` as MATLAB builds it (MathWorks' published COLONOP replication): the element count tolerates rounding of the end
+    point, the right end snaps to ``b`` when it is within 2 eps, and the vector is filled symmetrically from both ends
+    (``a + k d`` up to the middle, ``c - k d`` down from the right end, the exact mid-point ``(a + c) / 2`` for even n), so
+    the last bits differ from the naive ``a + d * (0:n)``."""
+    eps = np.finfo(float).eps
+    if not (np.isfinite(a) and np.isfinite(d) and np.isfinite(b)):
+        return np.array([np.nan])
+    if d == 0 or (a < b and d < 0) or (b < a and d > 0):
+        return np.zeros(0)
+    tol = 2.0 * eps * max(abs(a), abs(b))
+    sig = 1.0 if d > 0 else -1.0
+    if a == math.floor(a) and d == 1:
+        n = int(math.floor(b) - a)
+    elif a == math.floor(a) and d == math.floor(d):
+        q = math.floor(a / d)
+        r = a - q * d
+        n = int(math.floor((b - r) / d) - q)
+    else:
+        n = int(math.floor((b - a) / d + 0.5))
+        if sig * (a + n * d - b) > tol:
+            n -= 1
     if n < 0:
         return np.zeros(0)
-    return a + d * np.arange(n + 1)
+    c = a + n * d
+    if sig * (c - b) > -tol:
+        c = b
+    out = np.zeros(n + 1)
+    k = np.arange(n // 2 + 1)
+    out[k] = a + k * d
+    out[n - k] = c - k * d
+    if n % 2 == 0:
+        out[n // 2] = (a + c) / 2
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

@@ -81,3 +81,27 @@ def test_zero_v_rows_table():
 def test_grpdelay_is_17():
     b = mcode.FILTER_COEF_INT / 511.0
     assert mcode.grpdelay_mean_round(b) == 17       # MTD/fun_lss_pulse_compression.m:47
+
+
+def test_matlab_colon_follows_the_published_algorithm():
+    """``a:d:b`` (MTD/fun_MTD_produce.m:62-63 builds the ideal LFM time axes with it): element count with the end-point
+    tolerance, right end snapped to b, symmetric fill from both ends, exact mid-point for an even interval count --
+    MathWorks' published COLONOP replication, not ``a + d*(0:n)``."""
+    from oracle import mcode
+    from radar_signal_process_b200 import waveforms
+    assert np.array_equal(mcode.matlab_colon(0, 1, 5), np.arange(6.0))
+    assert np.array_equal(mcode.matlab_colon(1, 2, 10), np.array([1.0, 3, 5, 7, 9]))
+    assert mcode.matlab_colon(5, 1, 1).size == 0 and mcode.matlab_colon(0, 0, 1).size == 0
+    v = mcode.matlab_colon(0, 0.1, 1)
+    assert v.size == 11 and v[-1] == 1.0 and v[5] == 0.5                 # end snapped to b, mid-point (a + c) / 2
+    assert v[10 - 3] == 1.0 - 3 * 0.1 and v[3] == 3 * 0.1                # filled from both ends: 0.7 from the right (naive: 0.7000000000000001)
+    ts = 1 / 25e6
+    for tao in (0.28e-6, 8e-6, 28e-6):
+        t = mcode.matlab_colon(-tao / 2, ts, tao / 2 - ts)
+        assert t.size == int(round(tao / ts)) and t[0] == -tao / 2 and t[-1] == tao / 2 - ts
+        n = t.size - 1
+        kk = np.arange((n + 1) // 2)                                          # right half, the exact mid-point of an even n excluded
+        assert np.array_equal(t[n - kk], (tao / 2 - ts) - kk * ts) and np.array_equal(t[kk], -tao / 2 + kk * ts)
+        if n % 2 == 0:
+            assert t[n // 2] == (-tao / 2 + (tao / 2 - ts)) / 2
+        assert np.array_equal(t, waveforms._colon(-tao / 2, ts, tao / 2 - ts))     # the host mirror makes the same choice
