@@ -149,6 +149,8 @@ struct EnvSwitches {
     bool no_tma = false, no_tma_mtd = false, no_fused = false, no_fused_v = false, mega = false, no_cfar_tile = false;
     bool coexist = false;       // RB200_COEXIST=1: 12-warp pcw_kernel + one mtd64_tma CTA per SM, so that K1 of chunk i+1 and K2 of chunk i share the SMs
     bool mtd_tc = false;        // RB200_MTD_TC=1 (with RB200_NO_FUSED=1): P = 64 Doppler transform on the tensor cores (experiment, mtd64_tc_kernel.cu)
+    int split = 0;              // RB200_SPLIT=n: pcw_kernel on n SMs and mtd64_tma on the others at the same time, K2 consuming each CPI as soon
+                                // as K1 has finished it (the intermediate is then read from L2); experiment, device-resident batches only
     bool no_pcw = false;        // RB200_NO_PCW=1: the CTA-wide pc_fft_tma_kernel instead of the warp-private pcw_kernel
     bool onepass = false;       // RB200_ONEPASS=1: the single-pass kernel (PC intermediate in shared memory, onepass_kernel.cu)
     int op_dbg = 0;             // RB200_OP_DBG: timing experiments of the single-pass kernel (results are wrong)
@@ -162,6 +164,7 @@ struct EnvSwitches {
         no_pcw = flag("RB200_NO_PCW");
         coexist = flag("RB200_COEXIST");
         mtd_tc = flag("RB200_MTD_TC");
+        split = num("RB200_SPLIT");
         no_tma_mtd = flag("RB200_NO_TMA_MTD");
         no_fused = flag("RB200_NO_FUSED");
         no_fused_v = flag("RB200_NO_FUSED_V");
@@ -192,6 +195,7 @@ struct rb200_ctx {
     DevBuf raw, pc, rdm, dets_v, dets_2d, counters, vmask, errflag, colmask;
     DevBuf dbf_w;                  // DBF weights float2 [beam][channel]; dbf_beams = 0 when off
     int dbf_beams = 0;
+    DevBuf split_ctr;              // RB200_SPLIT: per-chunk progress counters and start flags
     DevBuf ring, megactr;          // fused persistent chain: L2-resident PC ring, work / completion counters
     bool last_was_mega = false;
     bool last_was_onepass = false;
@@ -411,8 +415,25 @@ static int build_plan(rb200_ctx* ctx, Plan& plan, const rb200_segment* segs, int
 }
 
 // run pulse compression: `in` wire int16 (n_groups = cpi*P groups of C lanes) or planar float2 (n_lines lines)
+// does run_pc take the warp-private pcw_kernel for this plan / input?
+static bool pcw_eligible(const rb200_ctx* ctx, const Plan& plan, bool wire, const void* in, int R, int C) {
+    if (!wire || plan.classes.size() != 1 || plan.classes[0].nt != 256 || ctx->env.no_tma || ctx->env.no_pcw ||
+        (reinterpret_cast<uintptr_t>(in) & 15) != 0)
+        return false;
+    PcParams q;
+    memset(&q, 0, sizeof q);
+    q.R = R;
+    q.C = C;
+    for (size_t i = 0; i < plan.segs.size(); ++i) {
+        if (plan.segs[i].nt != 256) return false;
+        q.segs[i] = plan.segs[i].d;
+    }
+    return pcw_plan_supported(q, (int)plan.segs.size(), plan.h_entries);
+}
+
 static int run_pc(rb200_ctx* ctx, const Plan& plan, bool wire, const void* in, float2* out, int R, int R_out,
-                  int C, int P, int n_groups_wire, int n_lines, const float* gain, cudaStream_t st) {
+                  int C, int P, int n_groups_wire, int n_lines, const float* gain, cudaStream_t st, int* cpi_done = nullptr,
+                  int* started = nullptr, int pcw_sms = 0) {
     if (!plan.valid) return fail(ctx, RB200_ERR_NO_WAVEFORM, "no waveform plan: call rb200_set_waveform first");
     if (plan.max_in_end > R) return fail(ctx, RB200_ERR_INDEX, "waveform segment exceeds the PRT length (Index exceeds array bounds)");
     if (plan.max_out_end > R_out) return fail(ctx, RB200_ERR_INDEX, "waveform segment output exceeds the PRT length");
@@ -442,14 +463,12 @@ static int run_pc(rb200_ctx* ctx, const Plan& plan, bool wire, const void* in, f
         const int lt = pc_tile_lanes(c.nt, wire);
         const int n_groups = wire ? n_groups_wire : (n_lines + lt - 1) / lt;
         if (n_groups <= 0) continue;
-        bool pcw_ok = wire && c.nt == 256 && plan.classes.size() == 1 && !ctx->env.no_tma && !ctx->env.no_pcw &&
-                      (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+        const bool pcw_ok = pcw_eligible(ctx, plan, wire, in, R, C);
         if (pcw_ok) {
-            for (auto& sp : plan.segs) pcw_ok &= (sp.nt == 256);
-            pcw_ok = pcw_ok && pcw_plan_supported(p, (int)plan.segs.size(), plan.h_entries);
+            p.cpi_done = cpi_done;
+            p.started = started;
+            CK(ctx, launch_pcw(p, c.n_tiles, n_groups, pcw_sms > 0 ? pcw_sms : ctx->n_sms, plan.h_entries, ctx->env.coexist, st));
         }
-        if (pcw_ok)
-            CK(ctx, launch_pcw(p, c.n_tiles, n_groups, ctx->n_sms, plan.h_entries, ctx->env.coexist, st));
         else if (wire && C == 16 && c.nt == 256 && plan.h_entries <= 2048 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && !ctx->env.no_tma)
             CK(ctx, launch_pc_fft_tma(p, c.n_tiles, n_groups, ctx->n_sms, ctx->pc_ctas_per_sm, plan.h_entries, st));
         else CK(ctx, launch_pc_fft(c.nt, wire, p, c.n_tiles, n_groups, st));
@@ -1664,10 +1683,26 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         // amplitudes of chunk i read it while chunk i+1 is already being transformed on another slot stream)
         if (rdm_host || !rdm_dev) CK(c, c->slots[i].rdm.ensure((size_t)G * cpi_cells * sizeof(float)));
     }
+    // RB200_SPLIT=n1 (experiment): pcw_kernel of every chunk on n1 SMs (stream A), mtd64_tma + range stage on the other SMs
+    // (stream B) at the same time; K2 fetches a tile only when K1 has counted the tile's CPI complete, so it reads the
+    // intermediate out of L2.  Device-resident input and output, default K1 / K2 kernels only.
+    const int n_chunks_total = (n_cpi + G - 1) / G;
+    const bool split_on = fused && !onepass && c->env.split > 0 && c->env.split < c->n_sms && raw_dev && !raw_host && !rdm_host && rdm_dev &&
+                          !c->stage_timing && dbf24_ch == 0 && !c->dbf_beams && !planar_in && (R % 2) == 0 && !c->env.no_tma_mtd &&
+                          pcw_eligible(c, c->plan, true, raw_dev, R, C);
+    int* split_done = nullptr;
+    int* split_started = nullptr;
+    if (split_on) {
+        CK(c, c->split_ctr.ensure((size_t)(n_cpi + n_chunks_total) * sizeof(int)));
+        CK(c, cudaMemsetAsync(c->split_ctr.p, 0, (size_t)(n_cpi + n_chunks_total) * sizeof(int), st));
+        split_done = c->split_ctr.as<int>();
+        split_started = split_done + n_cpi;
+    }
+    const int n_fork = split_on ? 2 : n_slots;
     CK(c, cudaEventRecord(c->ev0, st));
-    if (n_slots > 1) {
+    if (n_fork > 1) {
         CK(c, cudaEventRecord(c->fork_ev, st));
-        for (int i = 0; i < n_slots; ++i) CK(c, cudaStreamWaitEvent(c->slots[i].stream, c->fork_ev, 0));
+        for (int i = 0; i < n_fork; ++i) CK(c, cudaStreamWaitEvent(c->slots[i].stream, c->fork_ev, 0));
     }
     int chunk_idx = 0;
     for (int c0 = 0; c0 < n_cpi; c0 += G, ++chunk_idx) {
@@ -1737,6 +1772,31 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
             CK(c, launch_dbf(raw_chunk, sl.beams.as<float2>(), c->dbf_w.as<float2>(), C, Cin, g * P, P, R, cs));
             c->launches++;
             rc = run_pc(c, c->plan, false, sl.beams.p, pc_buf, R, R, 1, P, 0, g * C * P, c->gain_n ? c->gain.as<float>() : nullptr, cs);
+        } else if (split_on) {
+            cudaStream_t sa = c->slots[0].stream, sb = c->slots[1].stream;
+            if (chunk_idx >= n_slots) CK(c, cudaStreamWaitEvent(sa, sl.done, 0));        // the slot's buffers are free again
+            rc = run_pc(c, c->plan, true, raw_chunk, pc_buf, R, R, C, P, g * P, 0, c->gain_n ? c->gain.as<float>() : nullptr, sa,
+                        split_done + c0, split_started + chunk_idx, c->env.split);
+            if (rc) return rc;
+            cp.cpi0 = c0;
+            m64.in = pc_buf;
+            m64.out = rdm_chunk;
+            m64.cpi0 = c0;
+            m64.dets = sl.vlist.p;
+            m64.det_count = sl.count.as<int>();
+            m64.colmask = sl.colmask.as<unsigned long long>();
+            m64.wait_done = split_done + c0;
+            m64.wait_target = c->plan.classes[0].n_tiles * P * 4;          // four warp tasks per (PRT, tile) item
+            m64.err_flag = c->errflag.as<int>();
+            CK(c, launch_wait_flag(split_started + chunk_idx, c->errflag.as<int>(), sb));
+            CK(c, launch_mtd64_tma(m64, g * C, c->n_sms - c->env.split, c->mtd_ctas_per_sm, sb));
+            CK(c, launch_cfar_r64(rdm_chunk, cp, (float)k.cfar_t_r, sl.vlist.p, sl.count.as<int>(), c->dets_v.p, c->dets_2d.p,
+                                  c->counters.as<int>(), sl.colmask.as<unsigned long long>(), R, c->errflag.as<int>(), c->n_sms * 16, sb));
+            CK(c, cudaEventRecord(sl.done, sb));
+            c->launches += 4;
+            c->last_chunk_cpis = g;
+            c->last_pc = pc_buf;
+            continue;
         } else {
             rc = run_pc(c, c->plan, true, raw_chunk, pc_buf, R, R, C, P, g * P, 0, c->gain_n ? c->gain.as<float>() : nullptr, cs);
         }
@@ -1787,8 +1847,8 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
         c->last_chunk_cpis = g;
         c->last_pc = pc_buf;
     }
-    if (n_slots > 1) {
-        for (int i = 0; i < n_slots; ++i) {
+    if (n_fork > 1) {
+        for (int i = 0; i < n_fork; ++i) {
             CK(c, cudaEventRecord(c->slots[i].done, c->slots[i].stream));
             CK(c, cudaStreamWaitEvent(st, c->slots[i].done, 0));
         }

@@ -47,6 +47,10 @@ struct PcParams {
     int C;                  // lanes interleaved in the wire format
     int P;                  // PRTs per CPI (wire output line mapping)
     int n_lines;            // planar: number of lines
+    // RB200_SPLIT (producer / consumer kernels on disjoint SMs): pcw_kernel publishes its progress, one increment per finished
+    // warp task in cpi_done[cpi of this launch], and sets *started when its first CTA runs (both null otherwise)
+    int* cpi_done;
+    int* started;
 };
 
 // Range segments of the CFAR (fun_CFARflag, CW/main_cfar.m:142-161): the range stage never looks across a segment border
@@ -119,6 +123,10 @@ struct Mtd64Params {
     int cols_ld;
     int max_det, n_lanes, cpi0;
     CfarSegs segs;          // velocity hits in columns outside every segment are dropped
+    // RB200_SPLIT: a tile of CPI c (of this launch) is fetched only when wait_done[c] >= wait_target (null = no waiting)
+    const int* wait_done;
+    int wait_target;
+    int* err_flag;          // set to 2 when that wait times out
 };
 
 // fused persistent chain for P = 64, 16 channels (chain64_kernel.cu)

@@ -36,6 +36,7 @@ int mtd_generic_max_p();
 bool mtd64_fused_supported(int P, int ref_v, int guard_v, int n0, int mti_lag);
 cudaError_t launch_mtd64(const Mtd64Params& p, int n_slabs, bool with_cfar, cudaStream_t st);
 cudaError_t launch_mtd64_tma(const Mtd64Params& p, int n_slabs, int n_sms, int ctas_per_sm, cudaStream_t st);   // persistent, TMA-staged tiles (even in_ld / cols)
+cudaError_t launch_wait_flag(const int* flag, int* err_flag, cudaStream_t st);     // RB200_SPLIT: stream waits until *flag != 0
 cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, const void* slot_v, int* slot_count, void* dets_v,
                             void* dets_2d, int* gcount, const unsigned long long* colmask, int cols_ld, int* err_flag, int n_blocks,
                             cudaStream_t st);

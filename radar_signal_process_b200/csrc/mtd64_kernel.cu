@@ -54,7 +54,7 @@ mtd64_kernel(const Mtd64Params p) {
 // HBM/L2 read stream overlaps the butterflies.  Needs 16-byte aligned rows (even in_ld and cols).
 __device__ __forceinline__ uint32_t m64_smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 
-template <int REF, int GUARD, int N0, bool CFAR>
+template <int REF, int GUARD, int N0, bool CFAR, int LD = 0, int METH = -1, bool ZROWS = true>
 __global__ void __launch_bounds__(128, RB200_MTD64_MINB)
 mtd64_tma_kernel(const Mtd64Params p, int tiles_per_slab, int n_items) {
     constexpr int P = 64;
@@ -98,10 +98,32 @@ mtd64_tma_kernel(const Mtd64Params p, int tiles_per_slab, int n_items) {
                      "l"(src), "r"(bytes), "r"(m64_smem_u32(&full_bar))
                      : "memory");
     };
+    // RB200_SPLIT: the producer kernel (pcw_kernel on other SMs) counts finished warp tasks per CPI; a copy thread fetches its
+    // row only when the item's CPI is complete (acquire load, bounded spin), then orders the peers' generic-proxy stores
+    // before its own async-proxy read
+    auto ready = [&](int item) {
+        if (!p.wait_done) return;
+        const int cpi = (item / tiles_per_slab) / p.n_lanes;
+        const int* flag = p.wait_done + cpi;
+        int spins = 0, v;
+        while (true) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v >= p.wait_target) break;
+            if (++spins > (1 << 24)) {
+                if (p.err_flag) atomicExch(p.err_flag, 2);
+                break;
+            }
+            __nanosleep(200);
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+    };
     int item = blockIdx.x;
     if (item < n_items) {
         if (t == 0) expect(item);
-        if (t < P) copy_row(item);
+        if (t < P) {
+            ready(item);
+            copy_row(item);
+        }
     }
     for (int it = 0; item < n_items; item += gridDim.x, ++it) {
         const int slab = item / tiles_per_slab;
@@ -122,9 +144,10 @@ mtd64_tma_kernel(const Mtd64Params p, int tiles_per_slab, int n_items) {
         if (next < n_items && t < P) {
             if (t == 0) expect(next);
             wait_bar(&empty_bar, (uint32_t)(it & 1));      // every thread of the CTA is done with the tile
+            ready(next);
             copy_row(next);
         }
-        mtd64_column<REF, GUARD, N0, CFAR>(v, p, slab, r, ok);
+        mtd64_column<REF, GUARD, N0, CFAR, LD, METH, ZROWS>(v, p, slab, r, ok);
     }
 }
 
@@ -276,24 +299,55 @@ cudaError_t launch_mtd64(const Mtd64Params& p, int n_slabs, bool with_cfar, cuda
     return cudaGetLastError();
 }
 
+// RB200_SPLIT: holds a stream until the producer kernel of a chunk is running (its CTAs are then resident, so the consumer
+// grid launched next on this stream can only take the SMs the producer left free)
+__global__ void wait_flag_kernel(const int* flag, int* err_flag) {
+    int spins = 0, v;
+    while (true) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v != 0) break;
+        if (++spins > (1 << 24)) {
+            if (err_flag) atomicExch(err_flag, 2);
+            break;
+        }
+        __nanosleep(500);
+    }
+}
+cudaError_t launch_wait_flag(const int* flag, int* err_flag, cudaStream_t st) {
+    wait_flag_kernel<<<1, 1, 0, st>>>(flag, err_flag);
+    return cudaGetLastError();
+}
+
+template <int LD, int METH, bool ZROWS>
+static cudaError_t launch_mtd64_tma_variant(const Mtd64Params& p, int tiles_per_slab, int n_items, int grid, size_t smem, cudaStream_t st) {
+    static size_t configured[64] = {};
+    static bool carve = false;
+    auto kern = mtd64_tma_kernel<5, 7, 0, true, LD, METH, ZROWS>;
+    cudaError_t ce = ensure_dynamic_smem(kern, smem, configured);
+    if (ce != cudaSuccess) return ce;
+    if (!carve) {       // lets a CTA of this kernel join an SM that pcw_shared_kernel configured for the maximum carve-out
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve = true;
+    }
+    kern<<<grid, 128, smem, st>>>(p, tiles_per_slab, n_items);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mtd64_tma(const Mtd64Params& p, int n_slabs, int n_sms, int ctas_per_sm, cudaStream_t st) {
     if (p.cols <= 0 || n_slabs <= 0) return cudaSuccess;
     const int tiles_per_slab = (p.cols + 127) / 128;
     const long long n_items = (long long)tiles_per_slab * n_slabs;
     if (n_items > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const size_t smem = 64 * 128 * sizeof(float2);
-    static size_t configured[64] = {};
-    cudaError_t ce = ensure_dynamic_smem(mtd64_tma_kernel<5, 7, 0, true>, smem, configured);
-    if (ce != cudaSuccess) return ce;
-    static bool carve = false;
-    if (!carve) {       // lets a CTA of this kernel join an SM that pcw_shared_kernel configured for the maximum carve-out
-        cudaFuncSetAttribute(mtd64_tma_kernel<5, 7, 0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        carve = true;
-    }
     const int per_sm = std::max(1, std::min(ctas_per_sm, RB200_MTD64_MINB));
     const int grid = (int)std::min<long long>(n_items, (long long)n_sms * per_sm);
-    mtd64_tma_kernel<5, 7, 0, true><<<grid, 128, smem, st>>>(p, tiles_per_slab, (int)n_items);
-    return cudaGetLastError();
+    bool zrows = false;
+    for (int i = 0; i < 64; ++i) zrows |= (p.keep[i] != 1.f);
+    // the headline geometry (4096 range cells per row, no zeroed rows at P = 64) gets compile-time store offsets, a compile-time
+    // method and no keep multiplications; everything else takes the general instantiation
+    if (p.out_ld == 4096 && !zrows && p.meth_v == 0) return launch_mtd64_tma_variant<4096, 0, false>(p, tiles_per_slab, (int)n_items, grid, smem, st);
+    if (p.out_ld == 4096 && !zrows && p.meth_v == 1) return launch_mtd64_tma_variant<4096, 1, false>(p, tiles_per_slab, (int)n_items, grid, smem, st);
+    return launch_mtd64_tma_variant<0, -1, true>(p, tiles_per_slab, (int)n_items, grid, smem, st);
 }
 
 cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, const void* slot_v, int* slot_count, void* dets_v,

@@ -74,6 +74,10 @@ __device__ __forceinline__ void pcw_body(const PcParams& p, const CUtensorMap& t
     for (int i = t; i < h_entries; i += kThreads) h_sm[(i & ~255) + (i & 15) * 16 + ((i >> 4) & 15)] = __ldg(p.hperm + i);
     __syncthreads();
 
+    if (p.started && blockIdx.x == 0 && t == 0) {
+        *reinterpret_cast<volatile int*>(p.started) = 1;
+        __threadfence();
+    }
     const int worker = (int)blockIdx.x * kSlots + slot;
     const int stride = (int)gridDim.x * kSlots;
     unsigned char* const tile_sm = tiles + slot * kTileBytes;
@@ -174,6 +178,13 @@ __device__ __forceinline__ void pcw_body(const PcParams& p, const CUtensorMap& t
                         oa[c] = a[j];
                         oa[c + ob] = b[j];
                     }
+                }
+            }
+            if (p.cpi_done) {                     // consumer kernels on other SMs wait for this count (RB200_SPLIT)
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(p.cpi_done + cpi, 1);
                 }
             }
         }

@@ -513,6 +513,38 @@ def test_chain_k1_variants_agree(lib, monkeypatch, env):
     _compare_flags(dets, out, B, C, P, R, lib)
 
 
+@pytest.mark.parametrize("n1", [100, 74])
+def test_chain_split_schedule_device_resident(lib, monkeypatch, n1):
+    """RB200_SPLIT=n1: K1 (pcw_kernel) on n1 SMs and K2 (mtd64_tma_kernel) on the remaining SMs at the same time, K2 fetching a
+    tile only when K1's per-CPI progress counter says the CPI is complete.  Same kernels, so RDM and detections of the
+    device-resident call are bit-identical to the ordinary back-to-back schedule, over several chunks and repeated calls."""
+    import torch
+    P, R, C, B = 64, 1500, 16, 7
+    raw, _ = synth.s3_batch(B, P=P, R=R, C=C, n_targets=4, r_lo=20, r_hi=R - 80)
+    ref = mcode.load_ref("refDDCDataMF1")
+    cfar = synth.cfar_tuple(synth.S3_CFAR)
+    dev = torch.device("cuda", 0)
+    raw_d = torch.from_numpy(np.ascontiguousarray(raw)).to(dev)
+
+    def run(ctx):
+        rdm_d = torch.zeros((B, C, P, R), dtype=torch.float32, device=dev)
+        stream = torch.cuda.Stream(dev)
+        with torch.cuda.stream(stream):
+            ctx.chain_enqueue(raw_d.data_ptr(), B, rdm_d.data_ptr(), stream.cuda_stream)
+            dets, n = ctx.chain_fetch()
+        stream.synchronize()
+        return rdm_d.cpu().numpy(), np.sort(dets, order=["cpi", "lane", "v", "r", "kind"]), n
+
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=2, max_det=1 << 20) as ctx:
+        rdm0, dets0, n0 = run(ctx)
+    monkeypatch.setenv("RB200_SPLIT", str(n1))
+    with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, chunk_cpi=2, max_det=1 << 20) as ctx:
+        for _ in range(3):
+            rdm1, dets1, n1_ = run(ctx)
+            assert n1_ == n0 and np.array_equal(rdm1, rdm0)
+            assert all(np.array_equal(dets1[f], dets0[f]) for f in dets0.dtype.names)
+
+
 def test_chain_single_pass_kernel_falls_back_outside_its_envelope(lib, monkeypatch):
     """With RB200_ONEPASS=1, configurations the single-pass kernel does not cover (13 lanes, a three-segment waveform, iSTC,
     R not a multiple of 4) silently take the slot pipeline and still match the oracle."""
