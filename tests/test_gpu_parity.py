@@ -545,6 +545,31 @@ def test_chain_split_schedule_device_resident(lib, monkeypatch, n1):
             assert all(np.array_equal(dets1[f], dets0[f]) for f in dets0.dtype.names)
 
 
+@pytest.mark.parametrize("R,use_stc,P", [(1032, False, 64), (1450, True, 64), (868, True, 32)])
+def test_chain_pcw_kernel_multi_segment_plans(lib, monkeypatch, R, use_stc, P):
+    """The warp-private K1 (pcw_kernel) on a THREE-segment waveform plan with 16 wire lanes and an even PRT length: FIR
+    segment with its delay and rotation, two matched-filter segments with different spectra (h_off), tiles that touch the
+    neighbouring segment (zeroed outside [0, in_len)), tiles before the PRT start (negative TMA coordinates) and the iSTC
+    gains (MP/fun_lss_pulse_compression.m:24-37, MP/fun_iSTC.m:14) -- against the oracle.  RB200_PC_NT=256 keeps the 160-tap
+    segment on 256-sample tiles (the plan would otherwise give it 4096-point tiles and K1 would fall back to pc_fft_kernel)."""
+    monkeypatch.setenv("RB200_PC_NT", "256")
+    C, B = 16, 2
+    ref = mcode.load_ref("refDDCDataMF1")
+    raw, _ = synth.s3_batch(B, P=P, R=R, C=C, ref=ref, n_targets=3, r_lo=20, r_hi=R - 80, seed0=4242)
+    p2, p3 = mcode.load_pulse_literals()
+    cfar = synth.cfar_tuple(synth.S3_CFAR) if P == 64 else (5, 7, 5.0, 0, 3, 2, 5.0, 0, 0, 1)
+    stc = synth.s5_stc_curve()[: min(1025, R)] if use_stc else None
+    out = vec.chain(raw, B, P, R, C, ("lss_mp", p2, p3), cfar, stc=stc, near_tol=RTOL)
+    with lib.Context(0, n_prt=P, n_range=R, n_lanes=C, max_cpi=B, max_det=1 << 21) as ctx:
+        ctx.set_waveform(lib.waveforms.segments_mp(R, p2, p3))
+        ctx.set_cfar(*cfar)
+        if stc is not None:
+            ctx.set_stc(stc)
+        rdm, dets, n = ctx.chain(raw, B)
+    print("pcw multi-segment RDM rel err %.2e" % _close(rdm, out["rdm"]))
+    _compare_flags(dets, out, B, C, P, R, lib)
+
+
 def test_chain_single_pass_kernel_falls_back_outside_its_envelope(lib, monkeypatch):
     """With RB200_ONEPASS=1, configurations the single-pass kernel does not cover (13 lanes, a three-segment waveform, iSTC,
     R not a multiple of 4) silently take the slot pipeline and still match the oracle."""
