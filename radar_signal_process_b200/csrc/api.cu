@@ -350,6 +350,9 @@ static int build_plan(rb200_ctx* ctx, Plan& plan, const rb200_segment* segs, int
         }
         if (sp.nt) {
             sp.d.V = s.kind == RB200_SEG_MF_CIRC ? sp.nt : sp.nt - L + 1;
+            // 256-sample tiles: an even number of valid lags keeps every tile's first sample on an even range cell, which the
+            // tensor-map loads of pcw_kernel need (rows of two range cells); costs at most one lag per tile
+            if (s.kind != RB200_SEG_MF_CIRC && sp.nt == 256 && sp.d.V > 2) sp.d.V &= ~1;
             sp.d.h_off = (int)h_total;
             h_total += sp.nt;
         }
