@@ -19,10 +19,7 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 #endif
 
 // The column work shared by both kernel variants: v[] holds the 64 windowed slow-time samples of range cell r.
-// LD > 0: the output row pitch as a compile-time constant (every RDM store is then base + immediate); METH 0 / 1: the
-// velocity-stage method (GO / SO) as a compile-time constant, -1: read from the parameter block; ZROWS false: the caller
-// guarantees that no output row is zeroed (all keep factors are 1), so the 64 multiplications are skipped.
-template <int REF, int GUARD, int N0, bool CFAR, int LD = 0, int METH = -1, bool ZROWS = true>
+template <int REF, int GUARD, int N0, bool CFAR>
 __device__ __forceinline__ void mtd64_column(float2 (&v)[64], const Mtd64Params& p, int slab, int r, bool ok) {
     constexpr int P = 64;
     // ---- 64-point DIF: step 1, radix-8 over j for every q (elements q + 8j), twiddle w64^(q*k0) ----
@@ -49,20 +46,13 @@ __device__ __forceinline__ void mtd64_column(float2 (&v)[64], const Mtd64Params&
 #pragma unroll
         for (int k1 = 0; k1 < 8; ++k1) {
             const int row = (k0 + 8 * k1 + P / 2) & (P - 1);
-            const float m = fast_sqrt(a[k1].x * a[k1].x + a[k1].y * a[k1].y);
-            mag[row] = ZROWS ? m * p.keep[row] : m;
+            mag[row] = fast_sqrt(a[k1].x * a[k1].x + a[k1].y * a[k1].y) * p.keep[row];
         }
     }
     if (ok) {
-        if (LD > 0) {
-            float* out = p.out + (size_t)slab * P * LD + r;
+        float* out = p.out + (size_t)slab * P * p.out_ld + r;
 #pragma unroll
-            for (int row = 0; row < P; ++row) out[row * LD] = mag[row];
-        } else {
-            float* out = p.out + (size_t)slab * P * p.out_ld + r;
-#pragma unroll
-            for (int row = 0; row < P; ++row) out[(size_t)row * p.out_ld] = mag[row];
-        }
+        for (int row = 0; row < P; ++row) out[(size_t)row * p.out_ld] = mag[row];
     }
     if (!CFAR) return;
 
@@ -86,7 +76,7 @@ __device__ __forceinline__ void mtd64_column(float2 (&v)[64], const Mtd64Params&
         }
         const float a = okL ? sl : sr;
         const float b = okR ? sr : sl;
-        const float mu = METH == 0 ? fmaxf(a, b) : METH == 1 ? fminf(a, b) : (p.meth_v == 0 ? fmaxf(a, b) : fminf(a, b));
+        const float mu = p.meth_v == 0 ? fmaxf(a, b) : fminf(a, b);
         if (mag[N0 + 1 + y] >= mu * p.tv_over_ref) hits |= 1ull << (N0 + 1 + y);
     }
     {

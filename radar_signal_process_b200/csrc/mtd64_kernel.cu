@@ -54,7 +54,7 @@ mtd64_kernel(const Mtd64Params p) {
 // HBM/L2 read stream overlaps the butterflies.  Needs 16-byte aligned rows (even in_ld and cols).
 __device__ __forceinline__ uint32_t m64_smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 
-template <int REF, int GUARD, int N0, bool CFAR, int LD = 0, int METH = -1, bool ZROWS = true>
+template <int REF, int GUARD, int N0, bool CFAR>
 __global__ void __launch_bounds__(128, RB200_MTD64_MINB)
 mtd64_tma_kernel(const Mtd64Params p, int tiles_per_slab, int n_items) {
     constexpr int P = 64;
@@ -147,7 +147,7 @@ mtd64_tma_kernel(const Mtd64Params p, int tiles_per_slab, int n_items) {
             ready(next);
             copy_row(next);
         }
-        mtd64_column<REF, GUARD, N0, CFAR, LD, METH, ZROWS>(v, p, slab, r, ok);
+        mtd64_column<REF, GUARD, N0, CFAR>(v, p, slab, r, ok);
     }
 }
 
@@ -318,36 +318,24 @@ cudaError_t launch_wait_flag(const int* flag, int* err_flag, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-template <int LD, int METH, bool ZROWS>
-static cudaError_t launch_mtd64_tma_variant(const Mtd64Params& p, int tiles_per_slab, int n_items, int grid, size_t smem, cudaStream_t st) {
-    static size_t configured[64] = {};
-    static bool carve = false;
-    auto kern = mtd64_tma_kernel<5, 7, 0, true, LD, METH, ZROWS>;
-    cudaError_t ce = ensure_dynamic_smem(kern, smem, configured);
-    if (ce != cudaSuccess) return ce;
-    if (!carve) {       // lets a CTA of this kernel join an SM that pcw_shared_kernel configured for the maximum carve-out
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        carve = true;
-    }
-    kern<<<grid, 128, smem, st>>>(p, tiles_per_slab, n_items);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_mtd64_tma(const Mtd64Params& p, int n_slabs, int n_sms, int ctas_per_sm, cudaStream_t st) {
     if (p.cols <= 0 || n_slabs <= 0) return cudaSuccess;
     const int tiles_per_slab = (p.cols + 127) / 128;
     const long long n_items = (long long)tiles_per_slab * n_slabs;
     if (n_items > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const size_t smem = 64 * 128 * sizeof(float2);
+    static size_t configured[64] = {};
+    static bool carve = false;
+    cudaError_t ce = ensure_dynamic_smem(mtd64_tma_kernel<5, 7, 0, true>, smem, configured);
+    if (ce != cudaSuccess) return ce;
+    if (!carve) {       // lets a CTA of this kernel join an SM that pcw_shared_kernel configured for the maximum carve-out
+        cudaFuncSetAttribute(mtd64_tma_kernel<5, 7, 0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve = true;
+    }
     const int per_sm = std::max(1, std::min(ctas_per_sm, RB200_MTD64_MINB));
     const int grid = (int)std::min<long long>(n_items, (long long)n_sms * per_sm);
-    bool zrows = false;
-    for (int i = 0; i < 64; ++i) zrows |= (p.keep[i] != 1.f);
-    // the headline geometry (4096 range cells per row, no zeroed rows at P = 64) gets compile-time store offsets, a compile-time
-    // method and no keep multiplications; everything else takes the general instantiation
-    if (p.out_ld == 4096 && !zrows && p.meth_v == 0) return launch_mtd64_tma_variant<4096, 0, false>(p, tiles_per_slab, (int)n_items, grid, smem, st);
-    if (p.out_ld == 4096 && !zrows && p.meth_v == 1) return launch_mtd64_tma_variant<4096, 1, false>(p, tiles_per_slab, (int)n_items, grid, smem, st);
-    return launch_mtd64_tma_variant<0, -1, true>(p, tiles_per_slab, (int)n_items, grid, smem, st);
+    mtd64_tma_kernel<5, 7, 0, true><<<grid, 128, smem, st>>>(p, tiles_per_slab, (int)n_items);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_cfar_r64(const float* rdm, const CfarParams& p, float t_r, const void* slot_v, int* slot_count, void* dets_v,
