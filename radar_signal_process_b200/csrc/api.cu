@@ -151,7 +151,6 @@ struct EnvSwitches {
     bool mtd_tc = false;        // RB200_MTD_TC=1 (with RB200_NO_FUSED=1): P = 64 Doppler transform on the tensor cores (experiment, mtd64_tc_kernel.cu)
     int split = 0;              // RB200_SPLIT=n: pcw_kernel on n SMs and mtd64_tma on the others at the same time, K2 consuming each CPI as soon
                                 // as K1 has finished it (the intermediate is then read from L2); experiment, device-resident batches only
-    int pcw_proxy = 0;          // RB200_PCW_PROXY=1: what-if timing experiment inside pcw_kernel (see pcw_kernel.cu)
     bool no_pcw = false;        // RB200_NO_PCW=1: the CTA-wide pc_fft_tma_kernel instead of the warp-private pcw_kernel
     bool onepass = false;       // RB200_ONEPASS=1: the single-pass kernel (PC intermediate in shared memory, onepass_kernel.cu)
     int op_dbg = 0;             // RB200_OP_DBG: timing experiments of the single-pass kernel (results are wrong)
@@ -166,7 +165,6 @@ struct EnvSwitches {
         coexist = flag("RB200_COEXIST");
         mtd_tc = flag("RB200_MTD_TC");
         split = num("RB200_SPLIT");
-        pcw_proxy = num("RB200_PCW_PROXY");
         no_tma_mtd = flag("RB200_NO_TMA_MTD");
         no_fused = flag("RB200_NO_FUSED");
         no_fused_v = flag("RB200_NO_FUSED_V");
@@ -197,7 +195,6 @@ struct rb200_ctx {
     DevBuf raw, pc, rdm, dets_v, dets_2d, counters, vmask, errflag, colmask;
     DevBuf dbf_w;                  // DBF weights float2 [beam][channel]; dbf_beams = 0 when off
     int dbf_beams = 0;
-    DevBuf proxy_out;              // RB200_PCW_PROXY scratch
     DevBuf split_ctr;              // RB200_SPLIT: per-chunk progress counters and start flags
     DevBuf ring, megactr;          // fused persistent chain: L2-resident PC ring, work / completion counters
     bool last_was_mega = false;
@@ -473,13 +470,6 @@ static int run_pc(rb200_ctx* ctx, const Plan& plan, bool wire, const void* in, f
         if (pcw_ok) {
             p.cpi_done = cpi_done;
             p.started = started;
-            if (ctx->env.pcw_proxy) {
-                const size_t need = (size_t)(n_groups / std::max(P, 1) + 1) * C * P * R_out * sizeof(float);
-                if (ctx->proxy_out.ensure(need) == cudaSuccess) {
-                    p.proxy = 1;
-                    p.proxy_out = ctx->proxy_out.as<float>();
-                }
-            }
             CK(ctx, launch_pcw(p, c.n_tiles, n_groups, pcw_sms > 0 ? pcw_sms : ctx->n_sms, plan.h_entries, ctx->env.coexist, st));
         }
         else if (wire && C == 16 && c.nt == 256 && plan.h_entries <= 2048 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && !ctx->env.no_tma)

@@ -51,10 +51,6 @@ struct PcParams {
     // warp task in cpi_done[cpi of this launch], and sets *started when its first CTA runs (both null otherwise)
     int* cpi_done;
     int* started;
-    // RB200_PCW_PROXY (what-if timing experiment, results of the proxy are garbage): after a task every warp executes a stand-in
-    // for 0.75 Doppler items (32 L2-resident loads of the previous CPI's output, ~900 instructions, 32 stores to proxy_out)
-    float* proxy_out;
-    int proxy;
 };
 
 // Range segments of the CFAR (fun_CFARflag, CW/main_cfar.m:142-161): the range stage never looks across a segment border

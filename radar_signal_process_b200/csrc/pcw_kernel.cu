@@ -42,57 +42,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                  : "memory");
 }
 
-// What-if experiment (RB200_PCW_PROXY): the instruction and memory mix of one split-column Doppler item (16 columns per warp,
-// two threads per column: 32 loads of 8 bytes, a 32-point FFT's worth of packed butterflies, 64 shuffles, 32 magnitudes, the
-// CFAR sums of 32 cells, 32 stores) executed between two pulse-compression tasks, to measure how much of K2's work would hide
-// in K1's idle issue slots if the two were one kernel.  The values are meaningless.
-__device__ __noinline__ void k2_proxy(const float2* __restrict__ src, size_t row_pitch, float* __restrict__ dst, size_t dst_pitch, int lane) {
-    float2 v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __ldcg(src + (size_t)(2 * i + (lane >> 4)) * row_pitch + (lane & 15));
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float2 a = v[i], b = v[i + 16];
-            v[i] = cadd(a, b);
-            v[i + 16] = cmul_s(csub(a, b), 0.92387953f, -0.38268343f);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {      // interleave so that the next stage pairs different elements
-            const float2 t = v[2 * i + 1];
-            v[2 * i + 1] = v[(2 * i + 17) & 31];
-            v[(2 * i + 17) & 31] = t;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        v[i].x += __shfl_xor_sync(0xffffffffu, v[i].y, 16);
-        v[i].y -= __shfl_xor_sync(0xffffffffu, v[i].x, 16);
-    }
-    float mag[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        float m;
-        const float q = v[i].x * v[i].x + v[i].y * v[i].y;
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(q));
-        mag[i] = m;
-    }
-    unsigned hits = 0u;
-#pragma unroll
-    for (int y = 0; y < 32; ++y) {
-        float sl = 0.f, sr = 0.f;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            sl += mag[(y + 20 + j) & 31];
-            sr += mag[(y + 8 + j) & 31];
-        }
-        hits |= (mag[y] >= fmaxf(sl, sr) * 1.0f ? 1u : 0u) << y;
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) __stcs(dst + (size_t)i * dst_pitch + (lane & 15) + 16 * (lane >> 4), mag[i] + (float)(hits & 1u));
-}
-
 template <bool GAIN, int kWarps>
 __device__ __forceinline__ void pcw_body(const PcParams& p, const CUtensorMap& tmap, int n_items, int n_tiles, int h_entries) {
     using namespace pcw;
@@ -230,13 +179,6 @@ __device__ __forceinline__ void pcw_body(const PcParams& p, const CUtensorMap& t
                         oa[c + ob] = b[j];
                     }
                 }
-            }
-            if (p.proxy && cpi > 0 && (it & 3) != 3) {
-                // stand-in for 0.75 Doppler items per task: reads the PREVIOUS CPI's freshly written output (L2-resident)
-                const int col0 = ((item * 4 + quad) * 16) % (p.R_out - 32);
-                const float2* src = p.out + ((size_t)(cpi - 1) * kLanes + c_lane) * p.P * p.R_out + col0;
-                float* dst = p.proxy_out + ((size_t)cpi * kLanes + c_lane) * p.P * p.R_out + col0;
-                k2_proxy(src, (size_t)p.R_out, dst, (size_t)p.R_out, lane);
             }
             if (p.cpi_done) {                     // consumer kernels on other SMs wait for this count (RB200_SPLIT)
                 __syncwarp();
