@@ -238,6 +238,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     if args.workload == "S1":
         return run_s1_reference(args)
+    if args.workload == "S2":
+        return run_s2_reference(args)
     big = P * R * C > 2 ** 24
     sample = 1 if big else max(1, args.ref_cpis)
     lanes = [0] if big else None                             # S5: one lane of one CPI per step, scaled by the lane count
@@ -386,6 +388,82 @@ def run_s1(args):
         line["cpu_baseline"] = {"value": 1.0 / dtc, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "one frame through oracle/vec.py (float64), %.1f s" % dtc}
         line["parity"] = {"rdm_rel_err": float(np.abs(mtd - want).max() / np.abs(want).max())}
+    print(json.dumps(line))
+
+
+# ---- configuration 2 (S2): MP/main.m simulated target + clutter, 8 PRT x 1024 range, fun_MTD_produce + executeCFAR -------------
+S2_NAME = "S2 frame 8 PRT x 1024 range (main.m simulated target + fun_add_clutter), fun_MTD_produce (segments 82/242/700) + executeCFAR 5/7/T5 x 2/1/T5"
+S2_METRIC = "frames/s (fun_MTD_produce + executeCFAR, 8 PRT x 1024 range, host doubles in and out)"
+S2_CFAR_ARGS = (5, 7, 5.0, 0, 2, 1, 5.0, 0, 0, 1)
+
+
+def run_s2_reference(args):
+    from oracle import mcode, synth
+    echo = synth.s2_frame()
+
+    def step():
+        mtd = mcode.fun_MTD_produce_mp(echo)
+        return mcode.executeCFAR(mtd, *S2_CFAR_ARGS)
+
+    step()
+    n = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = time.perf_counter() - t0
+    value = n / dt
+    print(json.dumps({"impl": "reference", "metric": S2_METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": n,
+                      "warmup": 1, "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f64", "data": "synthetic", "config": {"workload": S2_NAME},
+                      "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": "port",
+                                       "sample": "%d frames through oracle/mcode.py (the loop-faithful transcription)" % n},
+                      "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def run_s2(args):
+    """S2 on the GPU through the reference-facing host API (MP/main.m:204-215 call sequence): host doubles in and out, so the
+    figure is end to end; the frame is tiny (8 x 1024), i.e. this measures call latency, not throughput."""
+    import torch
+    import radar_signal_process_b200 as rsp
+    from oracle import synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    echo = np.asfortranarray(synth.s2_frame())
+
+    def step():
+        mtd = rsp.fun_MTD_produce(echo)
+        return mtd, rsp.executeCFAR(mtd, *S2_CFAR_ARGS)
+
+    for _ in range(max(args.warmup, 3)):
+        mtd, (flag, flagv) = step()
+    torch.cuda.synchronize()
+    n = max(args.steps, 50)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        mtd, (flag, flagv) = step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    value = n / dt
+    peak, peak_src = measured_peak()
+    alg = 8 * 1024 * (16 + 8)
+    line = {"metric": S2_METRIC, "value": value, "unit": "frames/s", "n_gpus": 1, "steps": n, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": S2_NAME, "note": "host-double API: value == e2e; latency-bound (about ten kernel launches and four small copies per frame)"},
+            "roofline": {"bound": "hbm", "kernel": "whole fun_MTD_produce + executeCFAR call sequence (launch- and copy-latency bound at this size)",
+                         "achieved": value * alg / 1e9, "peak": peak, "unit": "GB/s", "frac": value * alg / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 8 * 1024 * 16 + 8 * 1024 * 8, "d2h_bytes_per_step": 8 * 1024 * 8 * 3},
+            "gpu_launches": None, "detections_per_step": int(flag.sum())}
+    if not args.no_cpu_baseline:
+        from oracle import mcode
+        t0 = time.perf_counter()
+        want = mcode.fun_MTD_produce_mp(echo)
+        fo, fvo = mcode.executeCFAR(mtd, *S2_CFAR_ARGS)
+        dtc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 1.0 / dtc, "unit": "frames/s", "cores": 1, "kind": "port",
+                                "sample": "one frame through oracle/mcode.py (loop-faithful transcription), %.2f s" % dtc}
+        line["parity"] = {"rdm_rel_err": float(np.abs(mtd - want).max() / np.abs(want).max()),
+                          "flags_identical_on_gpu_rdm": bool(np.array_equal(flag, fo) and np.array_equal(flagv, fvo))}
     print(json.dumps(line))
 
 
@@ -711,8 +789,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="S3", choices=["S3", "S5", "S1"],
-                    help="S3: BASELINE headline (default); S5: DBF long-CPI sweep with iSTC + MTI; S1: config-1 frame through the MATLAB-layout API")
+    ap.add_argument("--workload", default="S3", choices=["S3", "S5", "S1", "S2"],
+                    help="S3: BASELINE headline (default); S5: DBF long-CPI sweep with iSTC + MTI; S1 / S2: config-1 / config-2 frame through the MATLAB-layout API")
     ap.add_argument("--cpis", type=int, default=0, help="CPIs per step per GPU (0 = workload default: S3 64 -> 1 GiB of raw input, S5 4)")
     ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic CPIs generated (tiled up to --cpis; 0 = workload default)")
     ap.add_argument("--chunk", type=int, default=0, help="CPIs per PC->MTD->CFAR pass (0 = library default)")
@@ -726,12 +804,14 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of CPI 0 of the timed step")
     ap.add_argument("--ncu", action="store_true", help="fill roofline.traffic from a short ncu sub-run of the dominant kernel")
     args = ap.parse_args()
-    if args.workload != "S1":
+    if args.workload not in ("S1", "S2"):
         select_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "S1":
         run_s1(args)
+    elif args.workload == "S2":
+        run_s2(args)
     else:
         run_gpu(args)
 
