@@ -107,31 +107,37 @@ __device__ __forceinline__ void pcw_body(const PcParams& p, const CUtensorMap& t
         const int2 tile = __ldg(&p.tiles[item - g * n_tiles]);
         const PcSegDev& sg = p.segs[tile.x];
         const int in_off = tile.y * sg.V - sg.pre;
-        float gn[GAIN ? 16 : 1];
-        if (GAIN) {                               // MP/fun_iSTC.m:14; issued before the wait so that the loads overlap it
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int rs = in_off + n1 + 16 * j;
-                gn[GAIN ? j : 0] = (rs >= 0 && rs < sg.in_len) ? __ldg(p.gain + sg.in_start + rs) : 0.f;
-            }
-        }
         mbar_wait(&full_bar[slot], (uint32_t)(it & 1));
         float2 a[16], b[16];
+        // iSTC gains (MP/fun_iSTC.m:14) are per range cell, shared by every PRT and lane: they stay L1-resident, so they are
+        // fetched right where they are used instead of being held in registers across the wait
+        const float* gp = GAIN ? p.gain + sg.in_start + in_off + n1 : nullptr;
         if (in_off >= 0 && in_off + kNT <= sg.in_len) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {        // x[n1 + 16 j] of both lines (FrameDataRead_xzr.m:154-156)
                 const uint2 w = rd[128 * j];
                 a[j] = unpack_tc(w.x);
                 b[j] = unpack_tc(w.y);
+                if (GAIN) {
+                    const float gj = __ldg(gp + 16 * j);
+                    a[j] = cscale(a[j], gj);
+                    b[j] = cscale(b[j], gj);
+                }
             }
         } else {                                  // samples outside the segment are zero (the tile may touch its neighbours)
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int rs = in_off + n1 + 16 * j;
+                const bool in = rs >= 0 && rs < sg.in_len;
                 uint2 w = make_uint2(0u, 0u);
-                if (rs >= 0 && rs < sg.in_len) w = rd[128 * j];
+                if (in) w = rd[128 * j];
                 a[j] = unpack_tc(w.x);
                 b[j] = unpack_tc(w.y);
+                if (GAIN) {
+                    const float gj = in ? __ldg(gp + 16 * j) : 0.f;
+                    a[j] = cscale(a[j], gj);
+                    b[j] = cscale(b[j], gj);
+                }
             }
         }
         // generic-proxy reads of the slot are ordered before its refill by the copy engine: fence, arrive [release]; the
@@ -142,13 +148,6 @@ __device__ __forceinline__ void pcw_body(const PcParams& p, const CUtensorMap& t
         if (quad == 0) {
             mbar_wait(&empty_bar[slot], (uint32_t)(it & 1));
             if (item + stride < n_items && lane == 0) issue(item + stride);
-        }
-        if (GAIN) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                a[j] = cscale(a[j], gn[GAIN ? j : 0]);
-                b[j] = cscale(b[j], gn[GAIN ? j : 0]);
-            }
         }
         pc_pair_transform(a, b, twr, h_sm + sg.h_off, n1, rowA + n1, rowB + n1, rowA + 17 * n1, rowB + 17 * n1);
         __syncwarp();                             // the rows are reused by the next item
