@@ -325,12 +325,15 @@ cudaError_t launch_mtd64_tma(const Mtd64Params& p, int n_slabs, int n_sms, int c
     if (n_items > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const size_t smem = 64 * 128 * sizeof(float2);
     static size_t configured[64] = {};
-    static bool carve = false;
+    static bool carve[64] = {};         // function attributes are per device
     cudaError_t ce = ensure_dynamic_smem(mtd64_tma_kernel<5, 7, 0, true>, smem, configured);
     if (ce != cudaSuccess) return ce;
-    if (!carve) {       // lets a CTA of this kernel join an SM that pcw_shared_kernel configured for the maximum carve-out
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!carve[dev]) {  // lets a CTA of this kernel join an SM that pcw_shared_kernel configured for the maximum carve-out
         cudaFuncSetAttribute(mtd64_tma_kernel<5, 7, 0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        carve = true;
+        carve[dev] = true;
     }
     const int per_sm = std::max(1, std::min(ctas_per_sm, RB200_MTD64_MINB));
     const int grid = (int)std::min<long long>(n_items, (long long)n_sms * per_sm);

@@ -247,11 +247,14 @@ cudaError_t launch_pcw(const PcParams& p, int n_tiles, int n_groups, int n_sms, 
     if (shared_sm) {
         // the SM must be configured for the maximum shared-memory carve-out while this kernel runs, or the Doppler CTA that is
         // meant to join it (64 KB) cannot be placed until the SM drains
-        static bool carve[2] = {false, false};
-        if (!carve[p.gain ? 1 : 0]) {
+        static bool carve[2][64] = {};            // function attributes are per device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (!carve[p.gain ? 1 : 0][dev]) {
             if (p.gain) cudaFuncSetAttribute(pcw_shared_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             else cudaFuncSetAttribute(pcw_shared_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            carve[p.gain ? 1 : 0] = true;
+            carve[p.gain ? 1 : 0][dev] = true;
         }
         ce = p.gain ? ensure_dynamic_smem(pcw_shared_kernel<true>, smem, configured[3]) : ensure_dynamic_smem(pcw_shared_kernel<false>, smem, configured[2]);
     }
