@@ -37,7 +37,7 @@
 #include "pcw_core.cuh"
 #include "kernels.h"
 #include "../../include/radar_b200.h"
-#include <cuda.h>
+#include "tmap.h"
 #include <algorithm>
 
 namespace rb {
@@ -380,25 +380,11 @@ cudaError_t launch_deinterleave(const void* raw, void* planar, int n_cpi, int R,
 
 // tensor map of the lane planes: 2-D, 8-byte elements, [rows = cpi*16*32 + lane*32 + prt pair][pitch]; box = 256 x 16
 static cudaError_t encode_planar_map(CUtensorMap* map, void* planar, int n_cpi, int R, int V) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
-        if (e != cudaSuccess) return e;
-        if (qres != cudaDriverEntryPointSuccess || !ptr) return cudaErrorNotSupported;
-        fn = reinterpret_cast<EncodeFn>(ptr);
-    }
     const int pitch = onepass_planar_pitch(R, V);
     const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)n_cpi * op::kLanes * 32};
     const cuuint64_t strides[1] = {(cuuint64_t)pitch * 8};
     const cuuint32_t box[2] = {(cuuint32_t)op::kNT, 16};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, planar, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+    return tensor_map_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, planar, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 cudaError_t launch_onepass(const OnePassParams& p, void* planar, int n_sms, cudaStream_t st) {

@@ -19,7 +19,7 @@
 #include "pc_core.cuh"
 #include "pcw_core.cuh"
 #include "kernels.h"
-#include <cuda.h>
+#include "tmap.h"
 #include <algorithm>
 
 namespace rb {
@@ -216,25 +216,11 @@ bool pcw_plan_supported(const PcParams& p, int n_segs, int h_entries) {
 }
 
 static cudaError_t encode_wire_map(CUtensorMap* map, const void* in, int R, int n_groups) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
-        if (e != cudaSuccess) return e;
-        if (qres != cudaDriverEntryPointSuccess || !ptr) return cudaErrorNotSupported;
-        fn = reinterpret_cast<EncodeFn>(ptr);
-    }
     // [group][range / 2][32 words]: a row is two range cells x 16 lanes x (I, Q) = 128 bytes
     const cuuint64_t dims[3] = {32, (cuuint64_t)(R / 2), (cuuint64_t)n_groups};
     const cuuint64_t strides[2] = {128, (cuuint64_t)R * 64};
     const cuuint32_t box[3] = {32, (cuuint32_t)(pcw::kNT / 2), 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+    return tensor_map_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 cudaError_t launch_pcw(const PcParams& p, int n_tiles, int n_groups, int n_sms, int h_entries, bool shared_sm, cudaStream_t st) {
