@@ -1514,7 +1514,10 @@ static int chain_enqueue(rb200_ctx* c, const int16_t* raw_dev, int n_cpi, float*
     }
     if (n_cpi < 1 || n_cpi > k.max_cpi) return fail(c, RB200_ERR_ARG, "chain: n_cpi must be in 1..max_cpi");
     if (k.cfar_n0 < 0) return fail(c, RB200_ERR_INDEX, "executeCFAR: Index in position 1 exceeds array bounds (MTD_0_num < 0)");
-    const int G = chunk_size(c, raw_host != nullptr || rdm_host != nullptr);
+    int G = chunk_size(c, raw_host != nullptr || rdm_host != nullptr);
+    // a batch that fits one default chunk still runs as two, so that the tail of one chunk's kernels overlaps the head of the
+    // next on the slot streams (measured: 64 CPIs as 2 x 32 run 3 % faster than as 1 x 64)
+    if (!c->env.chunk && c->cfg.chunk_cpi <= 0 && n_cpi >= 16 && n_cpi < 2 * G) G = (n_cpi + 1) / 2;
     const size_t cpi_cells = (size_t)P * R * C;
     const size_t raw_cells = (size_t)P * R * Cin;
     const size_t raw_cpi_bytes = dbf24_ch > 0 ? (size_t)P * d24_prt_bytes : raw_cells * 4;   // input bytes of one CPI
