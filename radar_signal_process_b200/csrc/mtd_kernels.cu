@@ -56,6 +56,10 @@ mtd_fast_kernel(const MtdParams p) {
     unsigned long long a0 = reinterpret_cast<unsigned long long>(p.in + (size_t)slab * P * p.in_ld + (ok ? r : 0) + (size_t)u * p.in_ld);
     const unsigned long long stepb = (unsigned long long)R * p.in_ld * sizeof(float2);
 
+    // window and first-stage twiddles of the CTA in shared memory (every later access is base + immediate): win_sm[prt],
+    // tw_sm[u][k] = w_P^(u k); filled while the data loads below are in flight
+    __shared__ float win_sm[P];
+    __shared__ float2 tw_sm[P];
     float2 v[R];
     if (MTI) {
         // x[p + lag] - x[p], the last `lag` pulses are zero (MP/fun_Process_MTI.m:20-22)
@@ -65,20 +69,33 @@ mtd_fast_kernel(const MtdParams p) {
         for (int j = 0; j < R; ++j) {
             float2 x = make_float2(0.f, 0.f);
             if (j * R < last) x = csub(__ldg(reinterpret_cast<const float2*>(a1)), __ldg(reinterpret_cast<const float2*>(a0)));
-            v[j] = cscale(x, __ldg(p.window + u + j * R));
+            v[j] = x;
             a0 += stepb;
             a1 += stepb;
         }
     } else {
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            v[j] = cscale(__ldg(reinterpret_cast<const float2*>(a0)), __ldg(p.window + u + j * R));
+            v[j] = __ldg(reinterpret_cast<const float2*>(a0));
             a0 += stepb;
         }
     }
-    Dft<R, -1>::run(v);
+    for (int i = threadIdx.x; i < P; i += TR * R) {
+        win_sm[i] = __ldg(p.window + i);
+        tw_sm[i] = __ldg(p.tw + (i / R) * (i % R));
+    }
+    __syncthreads();
+    {
+        const float* wu = win_sm + u;
 #pragma unroll
-    for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(p.tw + u * k));
+        for (int j = 0; j < R; ++j) v[j] = cscale(v[j], wu[j * R]);
+    }
+    Dft<R, -1>::run(v);
+    {
+        const float2* twu = tw_sm + u * R;
+#pragma unroll
+        for (int k = 1; k < R; ++k) v[k] = cmul(v[k], twu[k]);
+    }
 #pragma unroll
     for (int k = 0; k < R; ++k) sm[(u + k * R) * TR + rl] = v[k];
     __syncthreads();
@@ -102,14 +119,25 @@ mtd_fast_kernel(const MtdParams p) {
     if (CF != 0) __syncthreads();
     float* mag_u = mag_sm + u * TR + rl;               // row u of this thread's column
     if (CF == 0 && !ok) return;
+    if (zany) {                                            // warp-uniform (u is): only the few warps that own a zeroed row test
 #pragma unroll
-    for (int k1 = 0; k1 < R; ++k1) {
-        const int roff = k1 < R / 2 ? P / 2 + R * k1 : R * (k1 - R / 2);     // row - u, compile-time
-        float mag = mtd_fast_sqrt(v[k1].x * v[k1].x + v[k1].y * v[k1].y);
-        if (zany && u + roff >= p.zv_lo && u + roff <= p.zv_hi) mag = 0.f;
-        const unsigned long long oa = (k1 < R / 2 ? o_hi + k1 * ostep : o_lo + (k1 - R / 2) * ostep);
-        if (ok) *reinterpret_cast<float*>(oa) = mag;
-        if (CF != 0) mag_u[roff * TR] = mag;
+        for (int k1 = 0; k1 < R; ++k1) {
+            const int roff = k1 < R / 2 ? P / 2 + R * k1 : R * (k1 - R / 2);     // row - u, compile-time
+            float mag = mtd_fast_sqrt(v[k1].x * v[k1].x + v[k1].y * v[k1].y);
+            if (u + roff >= p.zv_lo && u + roff <= p.zv_hi) mag = 0.f;
+            const unsigned long long oa = (k1 < R / 2 ? o_hi + k1 * ostep : o_lo + (k1 - R / 2) * ostep);
+            if (ok) *reinterpret_cast<float*>(oa) = mag;
+            if (CF != 0) mag_u[roff * TR] = mag;
+        }
+    } else {
+#pragma unroll
+        for (int k1 = 0; k1 < R; ++k1) {
+            const int roff = k1 < R / 2 ? P / 2 + R * k1 : R * (k1 - R / 2);
+            const float mag = mtd_fast_sqrt(v[k1].x * v[k1].x + v[k1].y * v[k1].y);
+            const unsigned long long oa = (k1 < R / 2 ? o_hi + k1 * ostep : o_lo + (k1 - R / 2) * ostep);
+            if (ok) *reinterpret_cast<float*>(oa) = mag;
+            if (CF != 0) mag_u[roff * TR] = mag;
+        }
     }
     if (CF == 0) return;
     // ---- fused velocity-axis CA-CFAR (CW/executeCFAR.m:28, CW/Function_CFAR1D_sub.m:17-69) on the tile ----
