@@ -76,12 +76,14 @@ __device__ __forceinline__ void pc_pair_transform(float2 (&a)[16], float2 (&b)[1
         b[m] = rB[m];
     }
     Dft<16, -1>::run(a);                                            // a[j] = X[n1 + 16 j]
+    float2 hv[16];                                                  // spectrum values fetched under the second line's butterflies
+#pragma unroll
+    for (int j = 0; j < 16; ++j) hv[j] = h_blk[16 * j + n1];
     Dft<16, -1>::run(b);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const float2 h = h_blk[16 * j + n1];
-        a[j] = cmul_s(a[j], h.x, h.y);
-        b[j] = cmul_s(b[j], h.x, h.y);
+        a[j] = cmul_s(a[j], hv[j].x, hv[j].y);
+        b[j] = cmul_s(b[j], hv[j].x, hv[j].y);
     }
     Dft<16, +1>::run(a);
     Dft<16, +1>::run(b);
