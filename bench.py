@@ -494,7 +494,7 @@ def ncu_dram_bytes(regex, workload, cpis):
     if not shutil.which("ncu"):
         return None, "ncu not found"
     cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:" + regex, "-s", "1", "-c", "2",
-           "--csv", sys.executable, os.path.abspath(__file__), "--workload", workload, "--cpis", str(cpis), "--steps", "1", "--warmup", "1",
+           "--csv", sys.executable, os.path.abspath(__file__), "--workload", workload, "--cpis", str(cpis), "--chunk", str(cpis), "--steps", "1", "--warmup", "1",
            "--no-cpu-baseline", "--e2e-steps", "0", "--no-parity"]
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=600).stdout
