@@ -46,8 +46,8 @@ WORKLOADS = {
                metric="CPI frames/s (iSTC->PC->MTI->MTD->0v->CFAR, 256 PRT x 16384 range x 16 lanes int16)",
                kernel="pcw_kernel (K1: int16 unpack + iSTC + overlap-save pulse compression, warp-private lines)",
                ncu_regex="pcw_kernel",
-               kernel_mtd="mtd_fast_kernel<16,32,MTI,2> (K2: MTI + window + 256-point slow-time FFT + |.| + 0-v + fused velocity CFAR; the largest share of S5)",
-               ncu_regex_mtd="mtd_fast"),
+               kernel_mtd="mtd256_tma_kernel<MTI,2> (K2: persistent, TMA-staged tiles; MTI + window + 256-point slow-time FFT + |.| + 0-v + fused velocity CFAR; the largest share of S5)",
+               ncu_regex_mtd="mtd256_tma"),
 }
 W = dict(WORKLOADS["S3"])                 # the active workload (set in main)
 P, R, C = W["P"], W["R"], W["C"]

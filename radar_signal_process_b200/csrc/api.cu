@@ -614,6 +614,8 @@ static int run_mtd(rb200_ctx* ctx, const float2* in, float* out, int P, int in_l
     p.out_c = out_c;
     p.crop_lo = crop_lo;
     p.crop_hi = crop_hi;
+    p.n_sms = ctx->n_sms;
+    p.no_tma = ctx->env.no_tma_mtd ? 1 : 0;
     if (ctx->env.mtd_tc && P == 64 && mti_lag == 0 && !fv && !out_c) {
         // experiment: DFT-by-GEMM on tcgen05 (window, fftshift and the zero-velocity rows are folded into the matrix)
         if (mp->tc_zlo != p.zv_lo || mp->tc_zhi != p.zv_hi || !mp->tc_mat.p) {

@@ -104,6 +104,9 @@ struct MtdParams {
     int* det_count;
     uint32_t* vmask;
     int* err_flag;
+    // P = 256: SMs of the device for the persistent TMA-fed kernel (0 = use the one-tile-per-CTA kernel), RB200_NO_TMA_MTD
+    int n_sms;
+    int no_tma;
 };
 
 struct rb200_det_fwd;

@@ -20,6 +20,9 @@
 #include "radix.cuh"
 #include "kernels.h"
 #include "cfar_core.cuh"
+#include "pc_core.cuh"
+#include "tmap.h"
+#include <algorithm>
 #include "../../include/radar_b200.h"
 
 namespace rb {
@@ -39,52 +42,25 @@ __device__ __forceinline__ float mtd_fast_sqrt(float x) {
     return r;
 }
 
-// CF: 0 = no CFAR, 1 = fused velocity CFAR with run-time (ref, guard), 2 = fused with the reference's default
-// protection/reference cells (5 reference, 7 guard: CW/main_cfar.m:147-154) as compile-time constants.
-template <int R, int TR, bool MTI, int CF>
-__global__ void __launch_bounds__(TR * R, 2)
-mtd_fast_kernel(const MtdParams p) {
+// Everything after the loads, shared by the one-tile-per-CTA kernel and the persistent TMA-fed one: window, radix-R butterflies,
+// corner turn through `sm` ([P][TR] float2), second butterflies, |.|, zero-velocity rows, RDM stores and (CF != 0) the fused
+// velocity-axis CFAR on the magnitude tile that re-uses `sm`.  Contains CTA-wide barriers: every thread of the CTA calls it.
+// barrier of the thread group that works on one tile: the whole CTA, or one 512-thread half of it (named barrier)
+struct MtdCtaSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct MtdHalfSync {
+    int id;
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, 512;" ::"r"(id) : "memory"); }
+};
+struct MtdNoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+template <int R, int TR, int CF, class Sync, class Hook>
+__device__ __forceinline__ void mtd_fast_body(float2 (&v)[R], const MtdParams& p, float2* sm, const float* win_sm, const float2* tw_sm,
+                                              const int slab, const int r, const bool ok, const int u, const int rl, const Sync sync,
+                                              const Hook after_first_sync) {
     constexpr int P = R * R;
-    extern __shared__ float2 sm[];   // [P][TR]
-    const int rl = threadIdx.x % TR;
-    const int u = threadIdx.x / TR;
-    const int slab = blockIdx.y;
-    const int r = blockIdx.x * TR + rl;
-    const bool ok = r < p.cols;
-    // one 64-bit byte address per thread, then a constant byte stride: pulse u + j*R sits j*stepb bytes further on
-    // (kept as integers so that the compiler steps the address instead of re-deriving it from an element index)
-    unsigned long long a0 = reinterpret_cast<unsigned long long>(p.in + (size_t)slab * P * p.in_ld + (ok ? r : 0) + (size_t)u * p.in_ld);
-    const unsigned long long stepb = (unsigned long long)R * p.in_ld * sizeof(float2);
-
-    // window and first-stage twiddles of the CTA in shared memory (every later access is base + immediate): win_sm[prt],
-    // tw_sm[u][k] = w_P^(u k); filled while the data loads below are in flight
-    __shared__ float win_sm[P];
-    __shared__ float2 tw_sm[P];
-    float2 v[R];
-    if (MTI) {
-        // x[p + lag] - x[p], the last `lag` pulses are zero (MP/fun_Process_MTI.m:20-22)
-        unsigned long long a1 = a0 + (unsigned long long)p.mti_lag * p.in_ld * sizeof(float2);
-        const int last = P - p.mti_lag - u;            // pulse u + j*R is kept iff j*R < last
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-            float2 x = make_float2(0.f, 0.f);
-            if (j * R < last) x = csub(__ldg(reinterpret_cast<const float2*>(a1)), __ldg(reinterpret_cast<const float2*>(a0)));
-            v[j] = x;
-            a0 += stepb;
-            a1 += stepb;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-            v[j] = __ldg(reinterpret_cast<const float2*>(a0));
-            a0 += stepb;
-        }
-    }
-    for (int i = threadIdx.x; i < P; i += TR * R) {
-        win_sm[i] = __ldg(p.window + i);
-        tw_sm[i] = __ldg(p.tw + (i / R) * (i % R));
-    }
-    __syncthreads();
     {
         const float* wu = win_sm + u;
 #pragma unroll
@@ -98,7 +74,8 @@ mtd_fast_kernel(const MtdParams p) {
     }
 #pragma unroll
     for (int k = 0; k < R; ++k) sm[(u + k * R) * TR + rl] = v[k];
-    __syncthreads();
+    sync();
+    after_first_sync();
 #pragma unroll
     for (int j = 0; j < R; ++j) v[j] = sm[(u * R + j) * TR + rl];
     Dft<R, -1>::run(v);
@@ -116,7 +93,7 @@ mtd_fast_kernel(const MtdParams p) {
     // P/2 rows into the buffer so that window reads up to P/2 rows outside the tile stay inside the allocation
     // (those values are never used: the edge rule replaces the side that does not fit).
     float* mag_sm = reinterpret_cast<float*>(sm) + (P / 2) * TR;
-    if (CF != 0) __syncthreads();
+    if (CF != 0) sync();
     float* mag_u = mag_sm + u * TR + rl;               // row u of this thread's column
     if (CF == 0 && !ok) return;
     if (zany) {                                            // warp-uniform (u is): only the few warps that own a zeroed row test
@@ -142,7 +119,7 @@ mtd_fast_kernel(const MtdParams p) {
     if (CF == 0) return;
     // ---- fused velocity-axis CA-CFAR (CW/executeCFAR.m:28, CW/Function_CFAR1D_sub.m:17-69) on the tile ----
     // Thread (u, rl) decides rows [u*R, (u+1)*R) of column rl; the reference windows come from shared memory.
-    __syncthreads();
+    sync();
     const int nv = p.cf.v_hi - p.cf.v_lo;
     const int ref = CF == 2 ? 5 : p.cf.ref_v;
     const int guard = CF == 2 ? 7 : p.cf.guard_v;
@@ -253,6 +230,158 @@ mtd_fast_kernel(const MtdParams p) {
                 reinterpret_cast<uint4*>(p.dets)[slot] = d;
             }
         }
+    }
+}
+
+
+// CF: 0 = no CFAR, 1 = fused velocity CFAR with run-time (ref, guard), 2 = fused with the reference's default
+// protection/reference cells (5 reference, 7 guard: CW/main_cfar.m:147-154) as compile-time constants.
+template <int R, int TR, bool MTI, int CF>
+__global__ void __launch_bounds__(TR * R, 2)
+mtd_fast_kernel(const MtdParams p) {
+    constexpr int P = R * R;
+    extern __shared__ float2 sm[];   // [P][TR]
+    const int rl = threadIdx.x % TR;
+    const int u = threadIdx.x / TR;
+    const int slab = blockIdx.y;
+    const int r = blockIdx.x * TR + rl;
+    const bool ok = r < p.cols;
+    // one 64-bit byte address per thread, then a constant byte stride: pulse u + j*R sits j*stepb bytes further on
+    // (kept as integers so that the compiler steps the address instead of re-deriving it from an element index)
+    unsigned long long a0 = reinterpret_cast<unsigned long long>(p.in + (size_t)slab * P * p.in_ld + (ok ? r : 0) + (size_t)u * p.in_ld);
+    const unsigned long long stepb = (unsigned long long)R * p.in_ld * sizeof(float2);
+
+    // window and first-stage twiddles of the CTA in shared memory (every later access is base + immediate): win_sm[prt],
+    // tw_sm[u][k] = w_P^(u k); filled while the data loads below are in flight
+    __shared__ float win_sm[P];
+    __shared__ float2 tw_sm[P];
+    float2 v[R];
+    if (MTI) {
+        // x[p + lag] - x[p], the last `lag` pulses are zero (MP/fun_Process_MTI.m:20-22)
+        unsigned long long a1 = a0 + (unsigned long long)p.mti_lag * p.in_ld * sizeof(float2);
+        const int last = P - p.mti_lag - u;            // pulse u + j*R is kept iff j*R < last
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            float2 x = make_float2(0.f, 0.f);
+            if (j * R < last) x = csub(__ldg(reinterpret_cast<const float2*>(a1)), __ldg(reinterpret_cast<const float2*>(a0)));
+            v[j] = x;
+            a0 += stepb;
+            a1 += stepb;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            v[j] = __ldg(reinterpret_cast<const float2*>(a0));
+            a0 += stepb;
+        }
+    }
+    for (int i = threadIdx.x; i < P; i += TR * R) {
+        win_sm[i] = __ldg(p.window + i);
+        tw_sm[i] = __ldg(p.tw + (i / R) * (i % R));
+    }
+    __syncthreads();
+    mtd_fast_body<R, TR, CF>(v, p, sm, win_sm, tw_sm, slab, r, ok, u, rl, MtdCtaSync(), MtdNoHook());
+}
+
+// Persistent TMA-fed variant for P = 256 (the DBF-mode CPI): one CTA of 1 024 threads per SM, two HALVES of 512 threads that
+// each walk over their own (slab, 32-column) tiles with the arithmetic of mtd_fast_kernel<16, 32, ...> (mtd_fast_body, barriers
+// = named barriers of the half).  The 256 x 32 input tile of an item (64 KB) arrives through ONE tensor-map TMA load (3-D map
+// over [slab][prt][2 x range] floats; columns past `cols` are zero-filled by the copy engine) into a staging buffer the two
+// halves use in turn: as soon as a half has pulled its samples into registers (its first barrier) it starts the load of the
+// OTHER half's next tile, so that every tile is in flight while both halves run butterflies and CFAR -- 32 warps stay in
+// the arithmetic phases instead of alternating with exposed load phases.  The MTI difference x[p + lag] - x[p] reads both pulses
+// from the staged tile (the one-tile-per-CTA kernel fetches every row twice).  Generic-proxy reads of the staging buffer are
+// ordered before the async-proxy refill by fence.proxy.async + the half's barrier.
+namespace m256 {
+constexpr int kR = 16, kTR = 32, kP = 256;
+constexpr int kHalf = kR * kTR;                      // 512 threads work on one tile
+constexpr int kThreads = 2 * kHalf;
+constexpr int kTileBytes = kP * kTR * 8;             // 65 536
+constexpr int kSmemBytes = 3 * kTileBytes + 128;     // the staging tile + one exchange / magnitude buffer per half
+}  // namespace m256
+
+__device__ __forceinline__ void mtd_tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// starts the load of `item` into the staging tile; called by one thread once the previous user has released the tile
+struct Mtd256Issue {
+    const CUtensorMap* map;
+    float2* stage;
+    uint64_t* bar;
+    int item, tiles_per_slab;
+    bool on;
+    __device__ __forceinline__ void operator()() const {
+        if (!on) return;
+        const int slab = item / tiles_per_slab;
+        const int c0 = (item - slab * tiles_per_slab) * m256::kTR;
+        mbar_expect_tx(bar, (uint32_t)m256::kTileBytes);
+        mtd_tma_load_3d(stage, map, 2 * c0, 0, slab, bar);
+    }
+};
+
+template <bool MTI, int CF>
+__global__ void __launch_bounds__(m256::kThreads, 1)
+mtd256_tma_kernel(const __grid_constant__ MtdParams p, const __grid_constant__ CUtensorMap tmap, int tiles_per_slab, int n_items) {
+    using namespace m256;
+    extern __shared__ __align__(128) unsigned char m256_smem[];
+    unsigned char* const base = m256_smem + ((128u - (smem_u32(m256_smem) & 127u)) & 127u);
+    float2* const stage = reinterpret_cast<float2*>(base);                                      // [P][TR], both halves in turn
+    __shared__ float win_sm[kP];
+    __shared__ float2 tw_sm[kP];
+    __shared__ __align__(8) uint64_t full_bar[2];        // [half]: the half's next tile has landed in the staging buffer
+    const int half = threadIdx.x / kHalf;                // warp-uniform
+    const int t = threadIdx.x - half * kHalf;
+    float2* const sm = reinterpret_cast<float2*>(base + (1 + half) * kTileBytes);               // [P][TR] of this half
+    const int rl = t % kTR;
+    const int u = t / kTR;
+    if (threadIdx.x < 2) mbar_init(&full_bar[threadIdx.x], 1);
+    if (threadIdx.x == 0) mbar_fence_init();
+    if (threadIdx.x < kP) {
+        win_sm[threadIdx.x] = __ldg(p.window + threadIdx.x);
+        tw_sm[threadIdx.x] = __ldg(p.tw + (threadIdx.x / kR) * (threadIdx.x % kR));
+    }
+    __syncthreads();
+    // tiles are dealt to the halves in the order half 0 of the CTA, half 1, half 0, ...: use n of the staging buffer belongs to
+    // half n & 1 and is its item number n >> 1
+    const int worker = (int)blockIdx.x * 2 + half;
+    const int stride = (int)gridDim.x * 2;
+    const int other = (int)blockIdx.x * 2 + (half ^ 1);
+    const MtdHalfSync sync{1 + half};
+    if (threadIdx.x == 0) Mtd256Issue{&tmap, stage, &full_bar[0], worker, tiles_per_slab, worker < n_items}();
+    const float2* tl = stage + u * kTR + rl;             // pulse u of this thread's column; pulse u + j R is j R rows further on
+    int it = 0;
+#pragma unroll 1
+    for (int item = worker; item < n_items; item += stride, ++it) {
+        const int slab = item / tiles_per_slab;
+        const int r = (item - slab * tiles_per_slab) * kTR + rl;
+        const bool ok = r < p.cols;
+        mbar_wait(&full_bar[half], (uint32_t)(it & 1));
+        float2 v[kR];
+        if (MTI) {
+            // x[p + lag] - x[p], the last `lag` pulses are zero (MP/fun_Process_MTI.m:20-22)
+            const float2* tl2 = tl + p.mti_lag * kTR;
+            const int last = kP - p.mti_lag - u;            // pulse u + j*R is kept iff j*R < last
+#pragma unroll
+            for (int j = 0; j < kR; ++j) {
+                float2 x = make_float2(0.f, 0.f);
+                if (j * kR < last) x = csub(tl2[j * kR * kTR], tl[j * kR * kTR]);
+                v[j] = x;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kR; ++j) v[j] = tl[j * kR * kTR];
+        }
+        // the samples are in registers: order these generic-proxy reads before the refill that follows the half's first barrier
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // next user of the staging buffer: the other half's item `it` (half 0) or its item `it + 1` (half 1)
+        const int nxt = other + (it + half) * stride;
+        const Mtd256Issue hook{&tmap, stage, &full_bar[half ^ 1], nxt, tiles_per_slab, t == 0 && nxt < n_items};
+        mtd_fast_body<kR, kTR, CF>(v, p, sm, win_sm, tw_sm, slab, r, ok, u, rl, sync, hook);
+        sync();                                             // the magnitude tile in `sm` is dead; the half's next item may write it
     }
 }
 
@@ -471,11 +600,48 @@ static cudaError_t launch_fast(const MtdParams& p, int n_slabs, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// P = 256 through the persistent kernel: needs 16-byte aligned rows for the tensor map
+static cudaError_t launch_mtd256_tma(const MtdParams& p, int n_slabs, cudaStream_t st) {
+    using namespace m256;
+    if (n_slabs > 65535) return cudaErrorInvalidConfiguration;
+    if ((size_t)kP * p.in_ld >= (1ull << 31) || (size_t)kP * p.out_ld >= (1ull << 31)) return cudaErrorInvalidValue;
+    const int cf = !p.cfar_on ? 0 : (p.cf.ref_v == 5 && p.cf.guard_v == 7) ? 2 : 1;
+    if (p.cfar_on && 2 * (p.cf.ref_v + p.cf.guard_v) > kP) return cudaErrorInvalidValue;
+    if (p.mti_lag < 0 || p.mti_lag >= kP) return cudaErrorInvalidValue;
+    const int tiles_per_slab = (p.cols + kTR - 1) / kTR;
+    const long long n_items = (long long)tiles_per_slab * n_slabs;
+    if (n_items > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    alignas(64) CUtensorMap map;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.cols * 2, (cuuint64_t)kP, (cuuint64_t)n_slabs};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.in_ld * sizeof(float2), (cuuint64_t)kP * p.in_ld * sizeof(float2)};
+    const cuuint32_t box[3] = {2 * kTR, (cuuint32_t)kP, 1};
+    cudaError_t ce = tensor_map_encode_tiled(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (ce != cudaSuccess) return ce;
+    const int grid = (int)std::min<long long>((n_items + 1) / 2, p.n_sms);     // two tiles in flight per CTA
+#define RB_MTD256(MTI, CF)                                                                                     \
+    do {                                                                                                       \
+        static size_t configured[64] = {};                                                                     \
+        ce = ensure_dynamic_smem(mtd256_tma_kernel<MTI, CF>, (size_t)kSmemBytes, configured);                  \
+        if (ce != cudaSuccess) return ce;                                                                      \
+        mtd256_tma_kernel<MTI, CF><<<grid, kThreads, kSmemBytes, st>>>(p, map, tiles_per_slab, (int)n_items);  \
+    } while (0)
+    if (p.mti_lag > 0) {
+        if (cf == 0) RB_MTD256(true, 0); else if (cf == 1) RB_MTD256(true, 1); else RB_MTD256(true, 2);
+    } else {
+        if (cf == 0) RB_MTD256(false, 0); else if (cf == 1) RB_MTD256(false, 1); else RB_MTD256(false, 2);
+    }
+#undef RB_MTD256
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mtd(const MtdParams& p, int n_slabs, cudaStream_t st) {
     if (p.cols <= 0 || n_slabs <= 0) return cudaSuccess;
     const bool plain = p.in_rows == 0 && !p.no_shift && !p.out_c;
     if (p.P == 64 && plain) return launch_fast<8, 64>(p, n_slabs, st);
-    if (p.P == 256 && plain) return launch_fast<16, 32>(p, n_slabs, st);
+    if (p.P == 256 && plain) {
+        const bool tma_ok = p.n_sms > 0 && !p.no_tma && (p.in_ld % 2) == 0 && (reinterpret_cast<uintptr_t>(p.in) % 16) == 0;
+        return tma_ok ? launch_mtd256_tma(p, n_slabs, st) : launch_fast<16, 32>(p, n_slabs, st);
+    }
     if (p.P == 1536 || p.P == 2048) {
         const size_t smem = (size_t)p.P * 8 * sizeof(float2);
         dim3 grid((p.cols + 7) / 8, n_slabs, 1);

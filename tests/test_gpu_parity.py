@@ -513,6 +513,34 @@ def test_chain_k1_variants_agree(lib, monkeypatch, env):
     _compare_flags(dets, out, B, C, P, R, lib)
 
 
+@pytest.mark.parametrize("R,mti,use_cfar_default", [(2000, 30, True), (1000, 0, True), (1512, 30, False)])
+def test_chain_p256_doppler_kernels_agree(lib, monkeypatch, R, mti, use_cfar_default):
+    """P = 256: the persistent TMA-fed Doppler kernel (mtd256_tma_kernel: two 512-thread halves per SM that take turns on one
+    staging tile) against the one-tile-per-CTA mtd_fast_kernel behind RB200_NO_TMA_MTD=1.  Both run mtd_fast_body on the same
+    samples (MP/fun_Process_MTI.m:20-22, MP/fun_Process_MTD.m:20-30, CW/executeCFAR.m:28), so RDM, detection list and count
+    must be bit-identical -- over several items per half (R = 2000: 63 tiles x 15 slabs), a ragged last tile (cols % 32 != 0),
+    MTI on and off, and the run-time (ref, guard) CFAR variant."""
+    P, C, B = 256, 5, 3
+    ref = mcode.load_ref("refDBFDataMF1")
+    raw = np.stack([synth.s3_cpi(i, P=P, R=R, C=C, ref=ref, seed0=7100, r_lo=100, r_hi=R - 200, n_targets=3)[0] for i in range(B)])
+    cfg = dict(synth.S5_CFAR)
+    if not use_cfar_default:
+        cfg.update(refV=4, saveV=6)
+    cfar = synth.cfar_tuple(cfg)
+
+    def run():
+        with _chain_ctx(lib, P, R, C, B, lib.waveforms.segments_single(R, ref), cfar, mti_lag=mti, chunk_cpi=3, max_det=1 << 20) as ctx:
+            rdm, dets, n = ctx.chain(raw, B)
+        return rdm, np.sort(dets, order=["cpi", "lane", "v", "r", "kind"]), n
+
+    rdm0, dets0, n0 = run()
+    monkeypatch.setenv("RB200_NO_TMA_MTD", "1")
+    rdm1, dets1, n1 = run()
+    assert n0 == n1 and n0 > 0
+    assert np.array_equal(rdm0, rdm1)
+    assert all(np.array_equal(dets0[f], dets1[f]) for f in dets0.dtype.names)
+
+
 @pytest.mark.parametrize("n1", [100, 74])
 def test_chain_split_schedule_device_resident(lib, monkeypatch, n1):
     """RB200_SPLIT=n1: K1 (pcw_kernel) on n1 SMs and K2 (mtd64_tma_kernel) on the remaining SMs at the same time, K2 fetching a
