@@ -56,7 +56,7 @@ struct MtdHalfSync {
 struct MtdNoHook {
     __device__ __forceinline__ void operator()() const {}
 };
-template <int R, int TR, int CF, class Sync, class Hook>
+template <int R, int TR, int CF, bool PRE_SYNC, class Sync, class Hook>
 __device__ __forceinline__ void mtd_fast_body(float2 (&v)[R], const MtdParams& p, float2* sm, const float* win_sm, const float2* tw_sm,
                                               const int slab, const int r, const bool ok, const int u, const int rl, const Sync sync,
                                               const Hook after_first_sync) {
@@ -72,6 +72,9 @@ __device__ __forceinline__ void mtd_fast_body(float2 (&v)[R], const MtdParams& p
 #pragma unroll
         for (int k = 1; k < R; ++k) v[k] = cmul(v[k], twu[k]);
     }
+    // persistent callers: `sm` still holds the magnitude tile of the group's previous item until everybody has left its CFAR;
+    // waiting HERE rather than at the end of that item lets the early warps run this item's loads and first butterflies
+    if (PRE_SYNC) sync();
 #pragma unroll
     for (int k = 0; k < R; ++k) sm[(u + k * R) * TR + rl] = v[k];
     sync();
@@ -280,7 +283,7 @@ mtd_fast_kernel(const MtdParams p) {
         tw_sm[i] = __ldg(p.tw + (i / R) * (i % R));
     }
     __syncthreads();
-    mtd_fast_body<R, TR, CF>(v, p, sm, win_sm, tw_sm, slab, r, ok, u, rl, MtdCtaSync(), MtdNoHook());
+    mtd_fast_body<R, TR, CF, false>(v, p, sm, win_sm, tw_sm, slab, r, ok, u, rl, MtdCtaSync(), MtdNoHook());
 }
 
 // Persistent TMA-fed variant for P = 256 (the DBF-mode CPI): one CTA of 1 024 threads per SM, two HALVES of 512 threads that
@@ -380,8 +383,7 @@ mtd256_tma_kernel(const __grid_constant__ MtdParams p, const __grid_constant__ C
         // next user of the staging buffer: the other half's item `it` (half 0) or its item `it + 1` (half 1)
         const int nxt = other + (it + half) * stride;
         const Mtd256Issue hook{&tmap, stage, &full_bar[half ^ 1], nxt, tiles_per_slab, t == 0 && nxt < n_items};
-        mtd_fast_body<kR, kTR, CF>(v, p, sm, win_sm, tw_sm, slab, r, ok, u, rl, sync, hook);
-        sync();                                             // the magnitude tile in `sm` is dead; the half's next item may write it
+        mtd_fast_body<kR, kTR, CF, true>(v, p, sm, win_sm, tw_sm, slab, r, ok, u, rl, sync, hook);
     }
 }
 
